@@ -1,0 +1,66 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def baseline_params():
+    from nmrgnn_b200.params import GNNParams, baseline_path
+    return GNNParams.load(baseline_path())
+
+
+def rel_err(a, ref):
+    """max |a-ref|/|ref| over ref != 0 (the north-star's 1e-4 relative metric)."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    nz = ref != 0
+    if not nz.any():
+        return 0.0
+    return float(np.max(np.abs(a[nz] - ref[nz]) / np.abs(ref[nz])))
+
+
+def scaled_err(a, ref):
+    """max |a-ref| / max |ref| — error relative to the tensor's own scale."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(a - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+
+def tol_ratio(a, ref, rtol=1e-4, atol=1e-4):
+    """max over atoms of |a-ref| / (rtol*|ref| + atol): <= 1 means every peak is
+    within the north-star's 1e-4 relative tolerance (plus 1e-4 ppm absolute so a
+    peak that happens to sit near 0 ppm does not make the metric meaningless)."""
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.max(np.abs(a - ref) / (rtol * np.abs(ref) + atol))) if a.size else 0.0
