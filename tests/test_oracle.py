@@ -3,7 +3,7 @@ the reference's traced SavedModel graph (tools/make_golden.py)."""
 import numpy as np
 import pytest
 
-from conftest import load_golden, rel_err, scaled_err
+from conftest import load_golden, rel_err, scaled_err, tol_ratio
 from oracle import forward as orc
 
 CASES = ["g108m", "ring5_unit", "ring5_bonded", "prot300", "edge_cases64"]
@@ -50,10 +50,10 @@ def test_oracle_batched_equals_per_graph(baseline_params, name):
     g = load_golden(name)
     # graphs are independent: one forward over the concatenated batch == per-graph forwards
     y = orc.forward(baseline_params, g["atoms"], g["nlist"], g["edges"], g["inv_degree"])
-    assert rel_err(y, g["peaks"]) < 5e-5
+    assert tol_ratio(y, g["peaks"]) < 1.0 and tol_ratio(y, g["peaks_f64"]) < 1.0
     y2 = orc.forward_per_graph(baseline_params, g["atoms"], g["nlist"], g["edges"], g["inv_degree"],
                                g["graph_offsets"])
-    assert rel_err(y2, g["peaks"]) < 5e-5
+    assert tol_ratio(y2, g["peaks"]) < 1.0
 
 
 def test_reference_weak_pins(baseline_params):
