@@ -1,0 +1,163 @@
+/*
+ * nmrgnn_b200 — C ABI of the B200-native (sm_100a) GNN forward path.
+ *
+ * The reference (ur-whitelab/nmrgnn) has no FFI: its boundary for this path is
+ * the Python call `model((atoms, nlist, edges, inv_degree))` on the Keras model
+ * returned by `nmrgnn.load_model()` (nmrgnn/library.py:92-103,
+ * nmrgnn/model.py:245-274).  This header is the C boundary introduced beneath
+ * that call; nmrgnn_b200/_capi.py binds it with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no exceptions cross the boundary;
+ *   - every function returns NMRGNN_OK (0) or a negative nmrgnn_status;
+ *     nmrgnn_last_error() gives the message for the last failure on a handle;
+ *   - `mem` says where the caller's buffers live: NMRGNN_MEM_HOST (the library
+ *     copies in/out on its stream; pinned memory makes the copies asynchronous)
+ *     or NMRGNN_MEM_DEVICE (pointers are device pointers on the handle's GPU);
+ *   - `stream` is a cudaStream_t passed as void*.  NULL = the handle's own
+ *     stream and the call returns after the work has completed.  Non-NULL =
+ *     work is enqueued on that stream and the call returns immediately
+ *     (device buffers only); errors detected on the device (out-of-range
+ *     neighbour index) are then reported by nmrgnn_synchronize();
+ *   - a handle may be used by one host thread at a time; different handles
+ *     (e.g. one per GPU) are independent.
+ *   - all tensors are dense row-major; float = IEEE binary32; nlist = int32.
+ */
+#ifndef NMRGNN_B200_H
+#define NMRGNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMRGNN_ABI_VERSION 1
+
+typedef enum nmrgnn_status {
+  NMRGNN_OK = 0,
+  NMRGNN_ERR_BAD_DIMS = -1,   /* unsupported/inconsistent sizes or null pointers      */
+  NMRGNN_ERR_BAD_INDEX = -2,  /* nlist entry outside [0, n_atoms) (TF GatherV2 raises) */
+  NMRGNN_ERR_CUDA = -3,       /* CUDA runtime error; message in nmrgnn_last_error      */
+  NMRGNN_ERR_OOM = -4,        /* device allocation failed                              */
+  NMRGNN_ERR_NO_DEVICE = -5   /* no sm_100 device / kernels not loadable               */
+} nmrgnn_status;
+
+enum { NMRGNN_MEM_HOST = 0, NMRGNN_MEM_DEVICE = 1 };
+
+/* activation ids: keras names used by the reference's hyper-parameters
+ * (nmrgnn/model.py:33-36) */
+enum { NMRGNN_ACT_LINEAR = 0, NMRGNN_ACT_SOFTPLUS = 1, NMRGNN_ACT_RELU = 2, NMRGNN_ACT_TANH = 3 };
+
+/* Model geometry — the reference's hyper-parameters (nmrgnn/model.py:22-36) plus
+ * the element count fixed at GNNModel.build (model.py:236-243). */
+typedef struct nmrgnn_dims {
+  int32_t num_elem;        /* C: one-hot width of `atoms`                        */
+  int32_t atom_features;   /* F: atom_feature_size                               */
+  int32_t edge_features;   /* E: edge_feature_size                               */
+  int32_t edge_hidden;     /* H: edge_hidden_size == RBF count                   */
+  int32_t n_edge_fc;       /* edge_fc_layers (last one linear, H->E)             */
+  int32_t n_mp;            /* mp_layers                                          */
+  int32_t n_fc;            /* fc_layers (last one F->F/2, no residual)           */
+  int32_t mp_activation;   /* NMRGNN_ACT_*                                       */
+  int32_t fc_activation;   /* NMRGNN_ACT_*                                       */
+  float rbf_low;           /* RBFExpansion low  (nmrgnn/layers.py:126-129)       */
+  float rbf_high;          /* RBFExpansion high                                  */
+} nmrgnn_dims;
+
+typedef struct nmrgnn_handle nmrgnn_handle;
+
+/* Number of host float arrays nmrgnn_create expects for `dims`:
+ * 2*n_edge_fc + 1 + n_mp + 2*n_fc + 2 + 2. */
+int nmrgnn_num_weights(const nmrgnn_dims* dims);
+
+/* Create a model on CUDA device `device`.  `weights` are host pointers in this
+ * order (shapes row-major):
+ *   edge FC i = 0..n_edge_fc-1 : kernel [in,out], bias [out]   (in = H; out = H, last E)
+ *   embed kernel [C,F]                                          (Dense, no bias; model.py:241)
+ *   MP layer l = 0..n_mp-1     : w [F,F,E]  indexed (l,m,n)     (layers.py:11-18)
+ *   FC i = 0..n_fc-1           : kernel [F,out], bias [out]     (out = F, last F/2)
+ *   out kernel [F/2,C], out bias [C]                            (model.py:239)
+ *   peak_std [C], peak_avg [C]                                  (model.py:222-228,242-243)
+ * Replaces: tf.keras.models.load_model(...) reviving the SavedModel
+ * (nmrgnn/library.py:101-102). */
+int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_weights,
+                  int device, nmrgnn_handle** out);
+
+void nmrgnn_destroy(nmrgnn_handle* h);
+
+/* peaks[n_atoms] = GNNModel.call((atoms, nlist, edges, inv_degree), training=False)
+ * (nmrgnn/model.py:245-274).
+ *   atoms      float [n_atoms, C]
+ *   nlist      int32 [n_atoms, k]   indices into this call's atoms; padded slots must
+ *                                   hold a valid index (0 by convention) and edge 0
+ *   edges      float [n_atoms, k]   distances in nm; <= 0 marks a padded slot
+ *   inv_degree float [n_atoms]
+ * Independent graphs are batched by concatenation (nlist offset per graph).
+ * n_atoms == 0 is allowed (no work). */
+int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
+                   const float* inv_degree, int64_t n_atoms, int32_t k, float* peaks,
+                   int mem, void* stream);
+
+/* Per-block entry points (same `mem`/`stream` rules), one per reference layer,
+ * used by the parity tests and by callers that compose their own model. */
+
+/* EdgeFCBlock(RBFExpansion(edges) * mask) * mask   (model.py:251-261, layers.py:137-140)
+ *   edges float [n_edges] -> edge_features float [n_edges, E] */
+int nmrgnn_edge_features(nmrgnn_handle* h, const float* edges, int64_t n_edges,
+                         float* edge_features, int mem, void* stream);
+
+/* embed_layer(atoms): float [n_atoms, C] -> float [n_atoms, F]   (model.py:262) */
+int nmrgnn_embed(nmrgnn_handle* h, const float* atoms, int64_t n_atoms, float* nodes,
+                 int mem, void* stream);
+
+/* nodes_out = MPLayer_l([nodes_in, nlist, edge_features, inv_degree]) + nodes_in
+ * (layers.py:26-46 + the residual of model.py:167); nodes_out must not alias nodes_in. */
+int nmrgnn_mp_layer(nmrgnn_handle* h, int32_t layer, const float* nodes_in, const int32_t* nlist,
+                    const float* edge_features, const float* inv_degree, int64_t n_atoms, int32_t k,
+                    float* nodes_out, int mem, void* stream);
+
+/* peaks = readout(FCBlock(nodes), atoms)   (model.py:191-196, 268-273).
+ * fc_nodes (float [n_atoms, F/2]) may be NULL; if not, it receives FCBlock's output. */
+int nmrgnn_fc_readout(nmrgnn_handle* h, const float* nodes, const float* atoms, int64_t n_atoms,
+                      float* peaks, float* fc_nodes, int mem, void* stream);
+
+/* Device k-nearest-neighbour graph builder: the input producer of the path, i.e.
+ * what nmrdata.parse_universe + the inv_degree line compute on the host in the
+ * reference (nmrgnn/library.py:111-116, nmrgnn/main.py:239-242).
+ *   positions     float [n_atoms, 3] in nm (mem rules as above)
+ *   graph_offsets int64 [n_graphs + 1], ALWAYS a host pointer: atoms of graph g are
+ *                 rows graph_offsets[g] .. graph_offsets[g+1]-1
+ *   k             neighbours per atom (1..32); cutoff_nm <= 0 disables the cutoff
+ * Outputs (same `mem` as positions): nlist int32 [n_atoms,k] (batch-global indices,
+ * neighbours sorted by distance, self excluded; missing slots = the graph's first
+ * atom with distance 0), edges float [n_atoms,k] in nm, inv_degree float [n_atoms]
+ * = 1 / #(graph-local index > 0), 0 if none (library.py:115-116 semantics). */
+int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* graph_offsets,
+                     int64_t n_atoms, int64_t n_graphs, int32_t k, float cutoff_nm, int32_t* nlist,
+                     float* edges, float* inv_degree, int mem, void* stream);
+
+/* Runtime options (value semantics per name):
+ *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies. */
+int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value);
+
+/* Wait for everything enqueued through this handle on `stream` (NULL = own stream)
+ * and report deferred device-side errors (NMRGNN_ERR_BAD_INDEX). */
+int nmrgnn_synchronize(nmrgnn_handle* h, void* stream);
+
+/* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t nmrgnn_kernel_launches(const nmrgnn_handle* h);
+
+/* Which compute path the handle selected for its dims: "tcgen05-3xtf32" or "ffma". */
+const char* nmrgnn_compute_path(const nmrgnn_handle* h);
+
+/* Message for the last error on `h` (h == NULL: last error of a failed create). */
+const char* nmrgnn_last_error(const nmrgnn_handle* h);
+
+int nmrgnn_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMRGNN_B200_H */

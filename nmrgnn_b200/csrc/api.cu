@@ -1,0 +1,623 @@
+// C ABI of libnmrgnn_b200.so (see include/nmrgnn_b200.h).  Host-side orchestration:
+// weight upload/re-packing, workspace, kernel launches, error reporting.
+#include "../../include/nmrgnn_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels_ffma.cuh"
+#include "knn.cuh"
+
+using namespace nmr;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct nmrgnn_handle {
+  nmrgnn_dims d{};
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::string path = "ffma";
+  int64_t launches = 0;
+
+  // device weights (owned)
+  std::vector<float*> owned;
+  std::vector<const float*> edge_W, edge_b, fc_W, fc_b;
+  const float* embed = nullptr;
+  std::vector<const float*> mp_Wp;  // packed for the FFMA kernel
+  const float *out_W = nullptr, *out_b = nullptr, *peak_std = nullptr, *peak_avg = nullptr;
+  const float* centers = nullptr;
+  float gap = 0.f;
+
+  // workspace (grow-only)
+  DevBuf atoms, nlist, edges, invdeg, efeat, hA, hB, peaks, tmp_in, tmp_out;
+  int* err_flag = nullptr;        // device
+  int* err_flag_host = nullptr;   // pinned
+  bool fast_path = false;         // F=256, H=128, E<=4: tiled kernels available
+  bool force_ffma = false;
+  DevBuf pos, offs;
+};
+
+namespace {
+
+int fail(nmrgnn_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail((h), _e == cudaErrorMemoryAllocation ? NMRGNN_ERR_OOM : NMRGNN_ERR_CUDA,     \
+                  "%s failed: %s", #expr, cudaGetErrorString(_e));                             \
+  } while (0)
+
+int ensure(nmrgnn_handle* h, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return NMRGNN_OK;
+  if (b.p) CUDA_TRY(h, cudaFree(b.p));
+  b.p = nullptr;
+  b.cap = 0;
+  size_t want = bytes + bytes / 8 + 256;
+  CUDA_TRY(h, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return NMRGNN_OK;
+}
+
+int upload(nmrgnn_handle* h, const float* host, size_t n, const float** out) {
+  float* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, n * sizeof(float) + 16));
+  h->owned.push_back(d);
+  CUDA_TRY(h, cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return NMRGNN_OK;
+}
+
+// float32 grid exactly as tf.linspace evaluates it for float32 inputs:
+// start + step*i with a separately rounded multiply and add; last point = stop.
+void rbf_grid(float lo, float hi, int n, std::vector<float>& c, float& gap) {
+  c.resize(n);
+  if (n == 1) {
+    c[0] = lo;
+    gap = 0.f;
+    return;
+  }
+  volatile float step = (hi - lo) / (float)(n - 1);
+  for (int i = 0; i < n; ++i) {
+    volatile float prod = step * (float)i;
+    volatile float s = lo + prod;
+    c[i] = s;
+  }
+  c[n - 1] = hi;
+  volatile float g = c[1] - c[0];
+  gap = g;
+}
+
+bool dims_ok(const nmrgnn_dims& d) {
+  return d.num_elem >= 1 && d.num_elem <= 1024 && d.atom_features >= 2 && d.atom_features % 2 == 0 &&
+         d.edge_features >= 1 && d.edge_hidden >= 1 && d.n_edge_fc >= 2 && d.n_edge_fc <= MAX_DENSE &&
+         d.n_mp >= 0 && d.n_mp <= 64 && d.n_fc >= 1 && d.n_fc <= MAX_DENSE && d.mp_activation >= 0 &&
+         d.mp_activation <= 3 && d.fc_activation >= 0 && d.fc_activation <= 3;
+}
+
+struct Io {  // resolves caller buffers to device pointers for one call
+  nmrgnn_handle* h;
+  int mem;
+  cudaStream_t s;
+  int in(const void* src, size_t bytes, DevBuf& stage, const void** out) {
+    if (mem == NMRGNN_MEM_DEVICE || bytes == 0) {
+      *out = src;
+      return NMRGNN_OK;
+    }
+    int rc = ensure(h, stage, bytes);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(stage.p, src, bytes, cudaMemcpyHostToDevice, s));
+    *out = stage.p;
+    return NMRGNN_OK;
+  }
+  int out_buf(void* dst, size_t bytes, DevBuf& stage, void** out) {
+    if (mem == NMRGNN_MEM_DEVICE) {
+      *out = dst;
+      return NMRGNN_OK;
+    }
+    int rc = ensure(h, stage, bytes);
+    if (rc) return rc;
+    *out = stage.p;
+    return NMRGNN_OK;
+  }
+  int finish(void* dst, const void* dev, size_t bytes) {
+    if (mem == NMRGNN_MEM_DEVICE || bytes == 0) return NMRGNN_OK;
+    CUDA_TRY(h, cudaMemcpyAsync(dst, dev, bytes, cudaMemcpyDeviceToHost, s));
+    return NMRGNN_OK;
+  }
+};
+
+int begin_call(nmrgnn_handle* h, int mem, void* stream, cudaStream_t* s) {
+  if (!h) return NMRGNN_ERR_BAD_DIMS;
+  if (mem != NMRGNN_MEM_HOST && mem != NMRGNN_MEM_DEVICE) return fail(h, NMRGNN_ERR_BAD_DIMS, "bad mem flag %d", mem);
+  if (stream != nullptr && mem == NMRGNN_MEM_HOST)
+    return fail(h, NMRGNN_ERR_BAD_DIMS, "host buffers require stream == NULL (synchronous call)");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  *s = stream ? (cudaStream_t)stream : h->stream;
+  return NMRGNN_OK;
+}
+
+int end_call(nmrgnn_handle* h, void* stream, cudaStream_t s) {
+  CUDA_TRY(h, cudaGetLastError());
+  if (stream != nullptr) return NMRGNN_OK;  // asynchronous: caller synchronises
+  return nmrgnn_synchronize(h, nullptr);
+}
+
+int grid_for(const nmrgnn_handle* h, int64_t tiles, int per_sm) {
+  int64_t g = (int64_t)h->num_sms * per_sm;
+  return (int)(tiles < g ? (tiles < 1 ? 1 : tiles) : g);
+}
+
+// ------------------------------------------------------------------ launches
+int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
+                const int32_t* nlist, int64_t n_atoms) {
+  if (n_edges == 0) return NMRGNN_OK;
+  if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  EdgeArgs a{};
+  a.edges = edges;
+  a.out = out;
+  a.n_edges = n_edges;
+  a.centers = h->centers;
+  a.gap = h->gap;
+  a.n_layers = h->d.n_edge_fc;
+  a.act = h->d.fc_activation;
+  for (int i = 0; i < h->d.n_edge_fc; ++i) {
+    a.W[i] = h->edge_W[i];
+    a.b[i] = h->edge_b[i];
+  }
+  a.nlist = nlist;
+  a.n_atoms = n_atoms;
+  a.err_flag = h->err_flag;
+  const int64_t tiles = (n_edges + 127) / 128;
+  const int grid = grid_for(h, tiles, 2);
+#define EDGE_CASE(EE)                                                                              \
+  case EE:                                                                                         \
+    edge_mlp_ffma_kernel<EE><<<grid, EDGE_THREADS, edge_smem_bytes<EE>(), s>>>(a);                 \
+    break;
+  switch (h->d.edge_features) {
+    EDGE_CASE(1) EDGE_CASE(2) EDGE_CASE(3) EDGE_CASE(4)
+    default: return fail(h, NMRGNN_ERR_BAD_DIMS, "edge_features %d unsupported", h->d.edge_features);
+  }
+#undef EDGE_CASE
+  h->launches++;
+  return NMRGNN_OK;
+}
+
+int launch_embed(nmrgnn_handle* h, cudaStream_t s, const float* atoms, int64_t n, float* nodes) {
+  if (n == 0) return NMRGNN_OK;
+  const int C = h->d.num_elem, F = h->d.atom_features;
+  const int64_t blocks = (n + EMBED_ATOMS - 1) / EMBED_ATOMS;
+  embed_kernel<<<(unsigned)blocks, 256, EMBED_ATOMS * C * sizeof(float), s>>>(atoms, h->embed, nodes, n, C, F);
+  h->launches++;
+  return NMRGNN_OK;
+}
+
+int launch_mp(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in, const int32_t* nlist,
+              const float* efeat, const float* invdeg, int64_t n, int K, float* h_out) {
+  if (n == 0) return NMRGNN_OK;
+  if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  MpArgs a{};
+  a.h_in = h_in;
+  a.h_out = h_out;
+  a.nlist = nlist;
+  a.efeat = efeat;
+  a.inv_degree = invdeg;
+  a.Wp = h->mp_Wp[layer];
+  a.n_atoms = n;
+  a.K = K;
+  a.act = h->d.mp_activation;
+  const int64_t tiles = (n + 127) / 128;
+  const int grid = grid_for(h, tiles, 1);
+#define MP_CASE(EE)                                                                                \
+  case EE: {                                                                                       \
+    const size_t smem = mp_smem_bytes<EE>(K);                                                      \
+    if (smem > 227 * 1024) return fail(h, NMRGNN_ERR_BAD_DIMS, "neighbor_number %d too large", K); \
+    CUDA_TRY(h, cudaFuncSetAttribute(mp_layer_ffma_kernel<EE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    mp_layer_ffma_kernel<EE><<<grid, MP_THREADS, smem, s>>>(a);                                    \
+  } break;
+  switch (h->d.edge_features) {
+    MP_CASE(1) MP_CASE(2) MP_CASE(3) MP_CASE(4)
+    default: return fail(h, NMRGNN_ERR_BAD_DIMS, "edge_features %d unsupported", h->d.edge_features);
+  }
+#undef MP_CASE
+  h->launches++;
+  return NMRGNN_OK;
+}
+
+int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float* atoms, int64_t n, float* peaks,
+              float* fc_nodes) {
+  if (n == 0) return NMRGNN_OK;
+  if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  FcArgs a{};
+  a.nodes = nodes;
+  a.atoms = atoms;
+  a.peaks = peaks;
+  a.fc_nodes = fc_nodes;
+  a.n_atoms = n;
+  a.C = h->d.num_elem;
+  a.n_layers = h->d.n_fc;
+  a.act = h->d.fc_activation;
+  for (int i = 0; i < h->d.n_fc; ++i) {
+    a.W[i] = h->fc_W[i];
+    a.b[i] = h->fc_b[i];
+  }
+  a.Wo = h->out_W;
+  a.bo = h->out_b;
+  a.peak_std = h->peak_std;
+  a.peak_avg = h->peak_avg;
+  const int64_t tiles = (n + 127) / 128;
+  fc_readout_ffma_kernel<<<grid_for(h, tiles, 1), FC_THREADS, fc_smem_bytes(), s>>>(a);
+  h->launches++;
+  return NMRGNN_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int nmrgnn_abi_version(void) { return NMRGNN_ABI_VERSION; }
+
+int nmrgnn_num_weights(const nmrgnn_dims* d) {
+  if (!d) return NMRGNN_ERR_BAD_DIMS;
+  return 2 * d->n_edge_fc + 1 + d->n_mp + 2 * d->n_fc + 2 + 2;
+}
+
+const char* nmrgnn_last_error(const nmrgnn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t nmrgnn_kernel_launches(const nmrgnn_handle* h) { return h ? h->launches : 0; }
+
+const char* nmrgnn_compute_path(const nmrgnn_handle* h) { return h ? h->path.c_str() : ""; }
+
+void nmrgnn_destroy(nmrgnn_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (float* p : h->owned) cudaFree(p);
+  for (DevBuf* b : {&h->atoms, &h->nlist, &h->edges, &h->invdeg, &h->efeat, &h->hA, &h->hB, &h->peaks, &h->tmp_in,
+                    &h->tmp_out, &h->pos, &h->offs})
+    if (b->p) cudaFree(b->p);
+  if (h->err_flag) cudaFree(h->err_flag);
+  if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_weights, int device,
+                  nmrgnn_handle** out) {
+  if (!dims || !weights || !out) return fail(nullptr, NMRGNN_ERR_BAD_DIMS, "null argument");
+  *out = nullptr;
+  if (!dims_ok(*dims)) return fail(nullptr, NMRGNN_ERR_BAD_DIMS, "inconsistent nmrgnn_dims");
+  if (n_weights != nmrgnn_num_weights(dims))
+    return fail(nullptr, NMRGNN_ERR_BAD_DIMS, "expected %d weight arrays, got %d", nmrgnn_num_weights(dims), n_weights);
+  for (int i = 0; i < n_weights; ++i)
+    if (!weights[i]) return fail(nullptr, NMRGNN_ERR_BAD_DIMS, "weights[%d] is null", i);
+
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, NMRGNN_ERR_NO_DEVICE, "no CUDA device visible");
+  }
+  if (device < 0 || device >= n_dev) return fail(nullptr, NMRGNN_ERR_NO_DEVICE, "device %d out of range", device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, NMRGNN_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, NMRGNN_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+
+  nmrgnn_handle* h = new (std::nothrow) nmrgnn_handle();
+  if (!h) return fail(nullptr, NMRGNN_ERR_OOM, "host allocation failed");
+  h->d = *dims;
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  int rc = NMRGNN_OK;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    nmrgnn_destroy(h);
+    return code;
+  };
+#define TRY_RC(expr)            \
+  do {                          \
+    rc = (expr);                \
+    if (rc) return bail(rc);    \
+  } while (0)
+#define CUDA_RC(expr)                                                        \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) {                                                 \
+      fail(h, NMRGNN_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+      return bail(NMRGNN_ERR_CUDA);                                          \
+    }                                                                        \
+  } while (0)
+
+  CUDA_RC(cudaSetDevice(device));
+  CUDA_RC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_RC(cudaMalloc(&h->err_flag, sizeof(int)));
+  CUDA_RC(cudaMemset(h->err_flag, 0, sizeof(int)));
+  CUDA_RC(cudaMallocHost(&h->err_flag_host, sizeof(int)));
+  *h->err_flag_host = 0;
+
+  const int C = dims->num_elem, F = dims->atom_features, E = dims->edge_features, H = dims->edge_hidden;
+  const int F2 = F / 2;
+  int w = 0;
+  h->edge_W.resize(dims->n_edge_fc);
+  h->edge_b.resize(dims->n_edge_fc);
+  for (int i = 0; i < dims->n_edge_fc; ++i) {
+    const int outw = (i == dims->n_edge_fc - 1) ? E : H;
+    TRY_RC(upload(h, weights[w++], (size_t)H * outw, &h->edge_W[i]));
+    TRY_RC(upload(h, weights[w++], (size_t)outw, &h->edge_b[i]));
+  }
+  TRY_RC(upload(h, weights[w++], (size_t)C * F, &h->embed));
+  h->mp_Wp.resize(dims->n_mp);
+  {
+    // W'[(c, n, ll), m] = w[c*32+ll, m, n]: K-order matches the T slices the MP kernel builds
+    std::vector<float> packed((size_t)F * E * F);
+    for (int l = 0; l < dims->n_mp; ++l) {
+      const float* src = weights[w++];
+      if (F % 32 == 0) {
+        for (int c = 0; c < F / 32; ++c)
+          for (int n = 0; n < E; ++n)
+            for (int ll = 0; ll < 32; ++ll) {
+              const size_t krow = (size_t)c * 32 * E + (size_t)n * 32 + ll;
+              const float* s = src + ((size_t)(c * 32 + ll) * F) * E + n;
+              float* dst = packed.data() + krow * F;
+              for (int m = 0; m < F; ++m) dst[m] = s[(size_t)m * E];
+            }
+      } else {
+        for (int lf = 0; lf < F; ++lf)
+          for (int n = 0; n < E; ++n)
+            for (int m = 0; m < F; ++m) packed[((size_t)lf * E + n) * F + m] = src[((size_t)lf * F + m) * E + n];
+      }
+      TRY_RC(upload(h, packed.data(), packed.size(), &h->mp_Wp[l]));
+    }
+  }
+  h->fc_W.resize(dims->n_fc);
+  h->fc_b.resize(dims->n_fc);
+  for (int i = 0; i < dims->n_fc; ++i) {
+    const int outw = (i == dims->n_fc - 1) ? F2 : F;
+    TRY_RC(upload(h, weights[w++], (size_t)F * outw, &h->fc_W[i]));
+    TRY_RC(upload(h, weights[w++], (size_t)outw, &h->fc_b[i]));
+  }
+  TRY_RC(upload(h, weights[w++], (size_t)F2 * C, &h->out_W));
+  TRY_RC(upload(h, weights[w++], (size_t)C, &h->out_b));
+  TRY_RC(upload(h, weights[w++], (size_t)C, &h->peak_std));
+  TRY_RC(upload(h, weights[w++], (size_t)C, &h->peak_avg));
+  {
+    std::vector<float> c;
+    rbf_grid(dims->rbf_low, dims->rbf_high, H, c, h->gap);
+    TRY_RC(upload(h, c.data(), c.size(), &h->centers));
+  }
+
+  h->fast_path = (F == 256 && H == 128 && E >= 1 && E <= 4);
+  if (h->fast_path) {
+    CUDA_RC(cudaFuncSetAttribute(fc_readout_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc_smem_bytes()));
+    CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<1>()));
+    CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<2>()));
+    CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<3>()));
+    CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<4>()));
+  }
+  h->path = "ffma";
+#undef TRY_RC
+#undef CUDA_RC
+  *out = h;
+  return NMRGNN_OK;
+}
+
+int nmrgnn_synchronize(nmrgnn_handle* h, void* stream) {
+  if (!h) return NMRGNN_ERR_BAD_DIMS;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = stream ? (cudaStream_t)stream : h->stream;
+  CUDA_TRY(h, cudaMemcpyAsync(h->err_flag_host, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));
+  if (*h->err_flag_host != 0) {
+    *h->err_flag_host = 0;
+    CUDA_TRY(h, cudaMemsetAsync(h->err_flag, 0, sizeof(int), s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return fail(h, NMRGNN_ERR_BAD_INDEX, "nlist holds an index outside [0, n_atoms)");
+  }
+  return NMRGNN_OK;
+}
+
+int nmrgnn_edge_features(nmrgnn_handle* h, const float* edges, int64_t n_edges, float* edge_features, int mem,
+                         void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (n_edges < 0 || (n_edges > 0 && (!edges || !edge_features))) return fail(h, NMRGNN_ERR_BAD_DIMS, "bad arguments");
+  Io io{h, mem, s};
+  const void* d_edges;
+  void* d_out;
+  const size_t E = h->d.edge_features;
+  if ((rc = io.in(edges, n_edges * sizeof(float), h->edges, &d_edges))) return rc;
+  if ((rc = io.out_buf(edge_features, n_edges * E * sizeof(float), h->efeat, &d_out))) return rc;
+  if ((rc = launch_edge(h, s, (const float*)d_edges, n_edges, (float*)d_out, nullptr, 0))) return rc;
+  if ((rc = io.finish(edge_features, d_out, n_edges * E * sizeof(float)))) return rc;
+  return end_call(h, stream, s);
+}
+
+int nmrgnn_embed(nmrgnn_handle* h, const float* atoms, int64_t n_atoms, float* nodes, int mem, void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (n_atoms < 0 || (n_atoms > 0 && (!atoms || !nodes))) return fail(h, NMRGNN_ERR_BAD_DIMS, "bad arguments");
+  Io io{h, mem, s};
+  const void* d_atoms;
+  void* d_out;
+  const size_t C = h->d.num_elem, F = h->d.atom_features;
+  if ((rc = io.in(atoms, n_atoms * C * sizeof(float), h->atoms, &d_atoms))) return rc;
+  if ((rc = io.out_buf(nodes, n_atoms * F * sizeof(float), h->hA, &d_out))) return rc;
+  if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, (float*)d_out))) return rc;
+  if ((rc = io.finish(nodes, d_out, n_atoms * F * sizeof(float)))) return rc;
+  return end_call(h, stream, s);
+}
+
+int nmrgnn_mp_layer(nmrgnn_handle* h, int32_t layer, const float* nodes_in, const int32_t* nlist,
+                    const float* edge_features, const float* inv_degree, int64_t n_atoms, int32_t k,
+                    float* nodes_out, int mem, void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (layer < 0 || layer >= h->d.n_mp) return fail(h, NMRGNN_ERR_BAD_DIMS, "layer %d out of range", layer);
+  if (n_atoms < 0 || k < 1 || (n_atoms > 0 && (!nodes_in || !nlist || !edge_features || !inv_degree || !nodes_out)))
+    return fail(h, NMRGNN_ERR_BAD_DIMS, "bad arguments");
+  if (nodes_in == nodes_out && n_atoms > 0) return fail(h, NMRGNN_ERR_BAD_DIMS, "nodes_out must not alias nodes_in");
+  if (n_atoms >= ((int64_t)1 << 31)) return fail(h, NMRGNN_ERR_BAD_DIMS, "n_atoms exceeds int32 index range");
+  Io io{h, mem, s};
+  const void *d_in, *d_nl, *d_ef, *d_inv;
+  void* d_out;
+  const size_t F = h->d.atom_features, E = h->d.edge_features;
+  if ((rc = io.in(nodes_in, n_atoms * F * sizeof(float), h->hA, &d_in))) return rc;
+  if ((rc = io.in(nlist, n_atoms * k * sizeof(int32_t), h->nlist, &d_nl))) return rc;
+  if ((rc = io.in(edge_features, n_atoms * k * E * sizeof(float), h->efeat, &d_ef))) return rc;
+  if ((rc = io.in(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;
+  if ((rc = io.out_buf(nodes_out, n_atoms * F * sizeof(float), h->hB, &d_out))) return rc;
+  if ((rc = launch_mp(h, s, layer, (const float*)d_in, (const int32_t*)d_nl, (const float*)d_ef, (const float*)d_inv,
+                      n_atoms, k, (float*)d_out)))
+    return rc;
+  if ((rc = io.finish(nodes_out, d_out, n_atoms * F * sizeof(float)))) return rc;
+  return end_call(h, stream, s);
+}
+
+int nmrgnn_fc_readout(nmrgnn_handle* h, const float* nodes, const float* atoms, int64_t n_atoms, float* peaks,
+                      float* fc_nodes, int mem, void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (n_atoms < 0 || (n_atoms > 0 && (!nodes || !atoms || !peaks))) return fail(h, NMRGNN_ERR_BAD_DIMS, "bad arguments");
+  Io io{h, mem, s};
+  const void *d_nodes, *d_atoms;
+  void *d_peaks, *d_fc = nullptr;
+  const size_t C = h->d.num_elem, F = h->d.atom_features, F2 = F / 2;
+  if ((rc = io.in(nodes, n_atoms * F * sizeof(float), h->hA, &d_nodes))) return rc;
+  if ((rc = io.in(atoms, n_atoms * C * sizeof(float), h->atoms, &d_atoms))) return rc;
+  if ((rc = io.out_buf(peaks, n_atoms * sizeof(float), h->peaks, &d_peaks))) return rc;
+  if (fc_nodes && (rc = io.out_buf(fc_nodes, n_atoms * F2 * sizeof(float), h->tmp_out, &d_fc))) return rc;
+  if ((rc = launch_fc(h, s, (const float*)d_nodes, (const float*)d_atoms, n_atoms, (float*)d_peaks, (float*)d_fc)))
+    return rc;
+  if ((rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
+  if (fc_nodes && (rc = io.finish(fc_nodes, d_fc, n_atoms * F2 * sizeof(float)))) return rc;
+  return end_call(h, stream, s);
+}
+
+int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
+                   const float* inv_degree, int64_t n_atoms, int32_t k, float* peaks, int mem, void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (n_atoms < 0 || k < 1) return fail(h, NMRGNN_ERR_BAD_DIMS, "n_atoms=%lld k=%d invalid", (long long)n_atoms, (int)k);
+  if (n_atoms == 0) return NMRGNN_OK;
+  if (!atoms || !nlist || !edges || !inv_degree || !peaks) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
+  if (n_atoms >= ((int64_t)1 << 31)) return fail(h, NMRGNN_ERR_BAD_DIMS, "n_atoms exceeds int32 index range");
+  Io io{h, mem, s};
+  const size_t C = h->d.num_elem, F = h->d.atom_features, E = h->d.edge_features;
+  const void *d_atoms, *d_nl, *d_edges, *d_inv;
+  void* d_peaks;
+  if ((rc = io.in(atoms, n_atoms * C * sizeof(float), h->atoms, &d_atoms))) return rc;
+  if ((rc = io.in(nlist, n_atoms * k * sizeof(int32_t), h->nlist, &d_nl))) return rc;
+  if ((rc = io.in(edges, n_atoms * k * sizeof(float), h->edges, &d_edges))) return rc;
+  if ((rc = io.in(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;
+  if ((rc = io.out_buf(peaks, n_atoms * sizeof(float), h->peaks, &d_peaks))) return rc;
+  if ((rc = ensure(h, h->efeat, n_atoms * k * E * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->hA, n_atoms * F * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->hB, n_atoms * F * sizeof(float)))) return rc;
+
+  float* ef = (float*)h->efeat.p;
+  float* ha = (float*)h->hA.p;
+  float* hb = (float*)h->hB.p;
+  if ((rc = launch_edge(h, s, (const float*)d_edges, n_atoms * k, ef, (const int32_t*)d_nl, n_atoms))) return rc;
+  if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
+  for (int l = 0; l < h->d.n_mp; ++l) {
+    if ((rc = launch_mp(h, s, l, ha, (const int32_t*)d_nl, ef, (const float*)d_inv, n_atoms, k, hb))) return rc;
+    float* t = ha;
+    ha = hb;
+    hb = t;
+  }
+  if ((rc = launch_fc(h, s, ha, (const float*)d_atoms, n_atoms, (float*)d_peaks, nullptr))) return rc;
+  if ((rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
+  return end_call(h, stream, s);
+}
+
+int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
+  if (!h || !name) return NMRGNN_ERR_BAD_DIMS;
+  if (std::strcmp(name, "force_ffma") == 0) {
+    h->force_ffma = value != 0;
+    return NMRGNN_OK;
+  }
+  return fail(h, NMRGNN_ERR_BAD_DIMS, "unknown option '%s'", name);
+}
+
+int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* graph_offsets, int64_t n_atoms,
+                     int64_t n_graphs, int32_t k, float cutoff_nm, int32_t* nlist, float* edges, float* inv_degree,
+                     int mem, void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (n_atoms < 0 || n_graphs < 0 || k < 1 || k > KNN_KMAX || !graph_offsets)
+    return fail(h, NMRGNN_ERR_BAD_DIMS, "bad arguments (k must be 1..%d)", KNN_KMAX);
+  if (n_atoms == 0 || n_graphs == 0) return NMRGNN_OK;
+  if (!positions || !nlist || !edges || !inv_degree) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
+  if (n_atoms >= ((int64_t)1 << 31) || n_graphs > 2147483647) return fail(h, NMRGNN_ERR_BAD_DIMS, "batch too large");
+  int64_t max_n = 0;
+  if (graph_offsets[0] != 0 || graph_offsets[n_graphs] != n_atoms) return fail(h, NMRGNN_ERR_BAD_DIMS, "graph_offsets must span [0, n_atoms]");
+  for (int64_t g = 0; g < n_graphs; ++g) {
+    const int64_t n = graph_offsets[g + 1] - graph_offsets[g];
+    if (n < 0) return fail(h, NMRGNN_ERR_BAD_DIMS, "graph_offsets must be non-decreasing");
+    if (n > max_n) max_n = n;
+  }
+  if (max_n == 0) return NMRGNN_OK;
+  const int64_t chunks = (max_n + KNN_THREADS - 1) / KNN_THREADS;
+  if (chunks > 65535) return fail(h, NMRGNN_ERR_BAD_DIMS, "graph of %lld atoms is too large for the kNN builder", (long long)max_n);
+  Io io{h, mem, s};
+  const void* d_pos;
+  void *d_nl, *d_ed, *d_inv;
+  if ((rc = io.in(positions, n_atoms * 3 * sizeof(float), h->pos, &d_pos))) return rc;
+  if ((rc = ensure(h, h->offs, (n_graphs + 1) * sizeof(int64_t)))) return rc;
+  // pageable host source: the runtime stages it before returning, so the caller may free it
+  CUDA_TRY(h, cudaMemcpyAsync(h->offs.p, graph_offsets, (n_graphs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  if ((rc = io.out_buf(nlist, n_atoms * k * sizeof(int32_t), h->nlist, &d_nl))) return rc;
+  if ((rc = io.out_buf(edges, n_atoms * k * sizeof(float), h->edges, &d_ed))) return rc;
+  if ((rc = io.out_buf(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;
+  KnnArgs a{};
+  a.pos = (const float*)d_pos;
+  a.offsets = (const int64_t*)h->offs.p;
+  a.nlist = (int32_t*)d_nl;
+  a.edges = (float*)d_ed;
+  a.inv_degree = (float*)d_inv;
+  a.k = k;
+  a.cutoff2 = cutoff_nm > 0.f ? cutoff_nm * cutoff_nm : 0.f;
+  knn_graph_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(a);
+  h->launches++;
+  if ((rc = io.finish(nlist, d_nl, n_atoms * k * sizeof(int32_t)))) return rc;
+  if ((rc = io.finish(edges, d_ed, n_atoms * k * sizeof(float)))) return rc;
+  if ((rc = io.finish(inv_degree, d_inv, n_atoms * sizeof(float)))) return rc;
+  return end_call(h, stream, s);
+}
+
+}  // extern "C"
