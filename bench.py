@@ -341,7 +341,7 @@ def run_ours(args):
             "whole_forward": {"tflops": total_atoms / world * fl["total"] / (ms_step * 1e-3) / 1e12,
                               "flops_per_atom": fl["total"], "bytes_per_atom": by["total"]},
         }
-        cpu = cpu_baseline(batch)
+        cpu = None if args.skip_cpu_baseline else cpu_baseline(batch)
         line = {
             "metric": "atoms/sec MP-GNN forward", "value": value, "unit": "atoms/s",
             "graphs_per_s": world * GRAPHS_PER_GPU / (ms_step * 1e-3),
@@ -369,6 +369,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only (ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
