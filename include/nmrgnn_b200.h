@@ -138,6 +138,11 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
                      int64_t n_atoms, int64_t n_graphs, int32_t k, float cutoff_nm, int32_t* nlist,
                      float* edges, float* inv_degree, int mem, void* stream);
 
+/* Diagnostic: D[128,128] = A[128,64] @ W[64,128] (host buffers) on the tcgen05 building
+ * blocks (K-major 64B-swizzled operands, TMEM accumulator).  mode 0 = 3xTF32 split
+ * (fp32-level accuracy), mode 1 = single TF32 product. */
+int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float* D, int mode);
+
 /* Runtime options (value semantics per name):
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies. */
 int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value);

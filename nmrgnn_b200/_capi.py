@@ -21,7 +21,7 @@ EXPORTS = [
     "nmrgnn_abi_version", "nmrgnn_num_weights", "nmrgnn_create", "nmrgnn_destroy", "nmrgnn_forward",
     "nmrgnn_edge_features", "nmrgnn_embed", "nmrgnn_mp_layer", "nmrgnn_fc_readout", "nmrgnn_synchronize",
     "nmrgnn_kernel_launches", "nmrgnn_compute_path", "nmrgnn_last_error", "nmrgnn_knn_graph",
-    "nmrgnn_set_option",
+    "nmrgnn_set_option", "nmrgnn_selftest_gemm",
 ]
 
 
@@ -70,6 +70,7 @@ def load_library() -> C.CDLL:
     lib.nmrgnn_last_error.restype = C.c_char_p
     lib.nmrgnn_knn_graph.argtypes = [vp, fp, fp, i64, i64, i32, C.c_float, fp, fp, fp, C.c_int, vp]
     lib.nmrgnn_set_option.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.nmrgnn_selftest_gemm.argtypes = [vp, fp, fp, fp, C.c_int]
     if lib.nmrgnn_abi_version() != 1:
         raise ImportError("libnmrgnn_b200.so ABI version mismatch")
     _lib = lib
@@ -154,6 +155,14 @@ class Handle:
     def fc_readout(self, nodes, atoms, n_atoms, peaks, fc_nodes, mem, stream=None):
         self.check(self._lib.nmrgnn_fc_readout(self._h, _ptr(nodes), _ptr(atoms), n_atoms, _ptr(peaks),
                                                _ptr(fc_nodes), mem, stream))
+
+    def selftest_gemm(self, A: np.ndarray, W: np.ndarray, mode: int = 0) -> np.ndarray:
+        A = np.ascontiguousarray(A, np.float32)
+        W = np.ascontiguousarray(W, np.float32)
+        assert A.shape == (128, 64) and W.shape == (64, 128)
+        D = np.empty((128, 128), np.float32)
+        self.check(self._lib.nmrgnn_selftest_gemm(self._h, _ptr(A), _ptr(W), _ptr(D), mode))
+        return D
 
     def knn_graph(self, positions, graph_offsets, n_atoms, n_graphs, k, cutoff, nlist, edges, inv_degree, mem,
                   stream=None):

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "kernels_ffma.cuh"
+#include "kernels_tc.cuh"
 #include "knn.cuh"
 
 using namespace nmr;
@@ -52,6 +53,11 @@ struct nmrgnn_handle {
   bool fast_path = false;         // F=256, H=128, E<=4: tiled kernels available
   bool force_ffma = false;
   DevBuf pos, offs;
+  // tensor-core path (F=256, H=128, E<=8): pre-split, pre-swizzled operand images
+  bool tc_ok = false;
+  const uint8_t* edge_img = nullptr;    // [n_hidden][8][hi 8192 | lo 8192]
+  const uint8_t* edge_f_img = nullptr;  // [8][hi 1024 | lo 1024]
+  const float* edge_bias = nullptr;     // [n_hidden][128]
 };
 
 namespace {
@@ -93,6 +99,44 @@ int upload(nmrgnn_handle* h, const float* host, size_t n, const float** out) {
   CUDA_TRY(h, cudaMemcpy(d, host, n * sizeof(float), cudaMemcpyHostToDevice));
   *out = d;
   return NMRGNN_OK;
+}
+
+int upload_bytes(nmrgnn_handle* h, const void* host, size_t bytes, const uint8_t** out) {
+  void* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, bytes + 16));
+  h->owned.push_back((float*)d);
+  CUDA_TRY(h, cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  *out = (const uint8_t*)d;
+  return NMRGNN_OK;
+}
+
+// fp32 -> tf32 (round to nearest, ties away, like cvt.rna.tf32.f32) kept in fp32 layout
+float tf32_hi(float x) {
+  uint32_t u;
+  std::memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u += 0x1000u;
+  u &= 0xFFFFE000u;
+  float r;
+  std::memcpy(&r, &u, 4);
+  return r;
+}
+
+// B-operand images for the tcgen05 kernels.  W is [K][ldw] row-major (in -> out); the operand
+// tile has one 64-byte swizzled row per output feature n0..n0+rows_tile-1 (rows >= rows_valid are
+// zero) and 16 consecutive k per chunk.  Layout: [chunk][hi tile | lo tile], hi = tf32(w), lo = w - hi.
+void pack_sw64(const float* W, int K, int ldw, int n0, int rows_valid, int rows_tile, std::vector<uint8_t>& out) {
+  const int chunks = K / tc::BK;
+  const size_t tile = (size_t)rows_tile * 64;
+  out.assign((size_t)chunks * 2 * tile, 0);
+  for (int c = 0; c < chunks; ++c)
+    for (int n = 0; n < rows_valid; ++n)
+      for (int kk = 0; kk < tc::BK; ++kk) {
+        const float w = W[(size_t)(c * tc::BK + kk) * ldw + n0 + n];
+        const float hi = tf32_hi(w), lo = w - hi;
+        const size_t off = tc::sw64_offset(n, kk);
+        std::memcpy(out.data() + (size_t)c * 2 * tile + off, &hi, 4);
+        std::memcpy(out.data() + (size_t)c * 2 * tile + tile + off, &lo, 4);
+      }
 }
 
 // float32 grid exactly as tf.linspace evaluates it for float32 inputs:
@@ -180,6 +224,28 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
                 const int32_t* nlist, int64_t n_atoms) {
   if (n_edges == 0) return NMRGNN_OK;
   if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  if (h->tc_ok && !h->force_ffma) {
+    EdgeTcArgs t{};
+    t.edges = edges;
+    t.out = out;
+    t.n_edges = n_edges;
+    t.centers = h->centers;
+    t.gap = h->gap;
+    t.Wimg = h->edge_img;
+    t.Wfimg = h->edge_f_img;
+    t.bias = h->edge_bias;
+    t.bias_f = h->edge_b[h->d.n_edge_fc - 1];
+    t.n_hidden = h->d.n_edge_fc - 1;
+    t.E = h->d.edge_features;
+    t.act = h->d.fc_activation;
+    t.nlist = nlist;
+    t.n_atoms = n_atoms;
+    t.err_flag = h->err_flag;
+    const int64_t tiles = (n_edges + 127) / 128;
+    edge_mlp_tc_kernel<<<grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s>>>(t);
+    h->launches++;
+    return NMRGNN_OK;
+  }
   EdgeArgs a{};
   a.edges = edges;
   a.out = out;
@@ -423,7 +489,25 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<3>()));
     CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<4>()));
   }
-  h->path = "ffma";
+  h->tc_ok = h->fast_path && E <= 8 && dims->n_edge_fc >= 2;
+  if (h->tc_ok) {
+    const int n_hidden = dims->n_edge_fc - 1;
+    std::vector<uint8_t> img, all;
+    std::vector<float> bias((size_t)n_hidden * 128);
+    int wi = 0;
+    for (int l = 0; l < n_hidden; ++l, wi += 2) {
+      pack_sw64(weights[wi], H, H, 0, H, H, img);
+      all.insert(all.end(), img.begin(), img.end());
+      std::memcpy(bias.data() + (size_t)l * 128, weights[wi + 1], 128 * sizeof(float));
+    }
+    TRY_RC(upload_bytes(h, all.data(), all.size(), &h->edge_img));
+    pack_sw64(weights[wi], H, E, 0, E, 16, img);
+    TRY_RC(upload_bytes(h, img.data(), img.size(), &h->edge_f_img));
+    TRY_RC(upload(h, bias.data(), bias.size(), &h->edge_bias));
+    CUDA_RC(cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ETC_SMEM));
+    CUDA_RC(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+  }
+  h->path = h->tc_ok ? "tcgen05-3xtf32(edge)+ffma" : "ffma";
 #undef TRY_RC
 #undef CUDA_RC
   *out = h;
@@ -562,6 +646,27 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
   if ((rc = launch_fc(h, s, ha, (const float*)d_atoms, n_atoms, (float*)d_peaks, nullptr))) return rc;
   if ((rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
   return end_call(h, stream, s);
+}
+
+int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float* D, int mode) {
+  cudaStream_t s;
+  int rc = begin_call(h, NMRGNN_MEM_HOST, nullptr, &s);
+  if (rc) return rc;
+  if (!A || !W || !D) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
+  if (!h->tc_ok) return fail(h, NMRGNN_ERR_BAD_DIMS, "tensor-core path not available for this geometry");
+  std::vector<uint8_t> img;
+  pack_sw64(W, ST_K, 128, 0, 128, 128, img);
+  if ((rc = ensure(h, h->tmp_in, 128 * ST_K * sizeof(float) + img.size()))) return rc;
+  if ((rc = ensure(h, h->tmp_out, 128 * 128 * sizeof(float)))) return rc;
+  uint8_t* d_img = (uint8_t*)h->tmp_in.p;
+  float* d_A = (float*)(d_img + img.size());
+  CUDA_TRY(h, cudaMemcpyAsync(d_img, img.data(), img.size(), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaMemcpyAsync(d_A, A, 128 * ST_K * sizeof(float), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(h, cudaStreamSynchronize(s));  // img is a local vector
+  tc_selftest_kernel<<<1, 192, ST_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
+  h->launches++;
+  CUDA_TRY(h, cudaMemcpyAsync(D, h->tmp_out.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return end_call(h, nullptr, s);
 }
 
 int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {

@@ -254,3 +254,22 @@ def test_knn_graph_matches_host_builder(model):
     assert nl2[:300].max() < 300 and nl2[300:].min() >= 300
     nl_b, e_b = knn_graph_host(pos[:200], k)
     np.testing.assert_allclose(e2[300:], e_b, rtol=2e-5, atol=1e-6)
+
+
+def test_tcgen05_selftest_gemm(model):
+    """Building blocks of the tensor-core path: one 128x128x64 GEMM through swizzled smem
+    operands and a TMEM accumulator; 3xTF32 must be fp32-accurate, 1xTF32 must not be."""
+    rng = np.random.default_rng(3)
+    A = rng.normal(size=(128, 64)).astype(np.float32)
+    W = rng.normal(size=(64, 128)).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64)
+    scale = np.abs(ref).max()
+    d3 = model.handle.selftest_gemm(A, W, 0)
+    d1 = model.handle.selftest_gemm(A, W, 1)
+    e3 = np.abs(d3 - ref).max() / scale
+    e1 = np.abs(d1 - ref).max() / scale
+    e32 = np.abs((A @ W) - ref).max() / scale
+    print(f"selftest: 3xTF32 err {e3:.2e}, 1xTF32 err {e1:.2e}, fp32 err {e32:.2e}")
+    assert e1 < 5e-3, "tcgen05 GEMM structurally wrong (layout/descriptor)"
+    assert e3 < 2e-6, "3xTF32 split does not reach fp32-level accuracy"
+    assert e1 > 20 * e3
