@@ -282,27 +282,19 @@ def run_ours(args):
         step_e2e()
     _, wall_e2e, _ = timed(step_e2e, args.steps)
 
-    # per-kernel timing (CUDA events on the launching stream) for the roofline object
-    ef = torch.empty((n_atoms, K_NEIGH, 3), dtype=torch.float32, device=dev)
-    hA = torch.empty((n_atoms, 256), dtype=torch.float32, device=dev)
-    hB = torch.empty_like(hA)
-    h.edge_features(d_in[2], n_atoms * K_NEIGH, ef, _capi.MEM_DEVICE, sptr)
-    h.embed(d_in[0], n_atoms, hA, _capi.MEM_DEVICE, sptr)
-    kern = {}
-
-    def time_kernel(name, fn, reps):
-        for _ in range(2):
-            fn()
-        ms, _, _ = timed(fn, reps)
-        kern[name] = ms / reps
-
-    time_kernel("edge", lambda: h.edge_features(d_in[2], n_atoms * K_NEIGH, ef, _capi.MEM_DEVICE, sptr), args.steps)
-    time_kernel("embed", lambda: h.embed(d_in[0], n_atoms, hA, _capi.MEM_DEVICE, sptr), args.steps)
-    time_kernel("mp_layer",
-                lambda: h.mp_layer(1, hA, d_in[1], ef, d_in[3], n_atoms, K_NEIGH, hB, _capi.MEM_DEVICE, sptr),
-                args.steps * 2)
-    time_kernel("fc_readout", lambda: h.fc_readout(hA, d_in[0], n_atoms, d_peaks, None, _capi.MEM_DEVICE, sptr),
-                args.steps)
+    # per-kernel timing for the roofline object: CUDA events recorded by the library on the launching
+    # stream around each stage of the same forward (option "profile"), averaged over the timed steps
+    h.set_option("profile", 1)
+    acc = None
+    for _ in range(args.steps):
+        step_device()
+        st = h.stage_times()
+        flat = [st["edge"], st["embed"]] + list(st["mp_layers"]) + [st["fc_readout"]]
+        acc = flat if acc is None else [a + b for a, b in zip(acc, flat)]
+    h.set_option("profile", 0)
+    acc = [a / args.steps for a in acc]
+    n_mp = len(acc) - 3
+    kern = {"edge": acc[0], "embed": acc[1], "mp_layer": sum(acc[2:2 + n_mp]) / n_mp, "fc_readout": acc[-1]}
     h.synchronize(sptr)
 
     # max over ranks of the device time

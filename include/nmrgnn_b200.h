@@ -139,13 +139,21 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
                      float* edges, float* inv_degree, int mem, void* stream);
 
 /* Diagnostic: D[128,128] = A[128,64] @ W[64,128] (host buffers) on the tcgen05 building
- * blocks (K-major 64B-swizzled operands, TMEM accumulator).  mode 0 = 3xTF32 split
- * (fp32-level accuracy), mode 1 = single TF32 product. */
+ * blocks (K-major 64B-swizzled operands, TMEM accumulators).  mode 0 = 3xTF32 split in one
+ * accumulator, mode 1 = single TF32 product, mode 2 = FP16 scaled split with main/correction
+ * accumulators (the production scheme, fp32-level accuracy), mode 3 = single FP16 product. */
 int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float* D, int mode);
 
 /* Runtime options (value semantics per name):
- *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies. */
+ *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
+ *   "profile"    = 1: nmrgnn_forward records CUDA events (on the launching stream) around its
+ *                     stages; read them with nmrgnn_stage_times. */
 int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value);
+
+/* Device time (ms, CUDA events) of each stage of the last profiled nmrgnn_forward, in launch
+ * order: edge kernel, embed (+ per-atom max), MP layer 0..n_mp-1, FC+readout.  Waits for that
+ * forward to finish.  Returns the number of stages written (n_mp + 3) or a negative status. */
+int nmrgnn_stage_times(nmrgnn_handle* h, float* ms, int cap);
 
 /* Wait for everything enqueued through this handle on `stream` (NULL = own stream)
  * and report deferred device-side errors (NMRGNN_ERR_BAD_INDEX). */
@@ -154,7 +162,7 @@ int nmrgnn_synchronize(nmrgnn_handle* h, void* stream);
 /* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t nmrgnn_kernel_launches(const nmrgnn_handle* h);
 
-/* Which compute path the handle selected for its dims: "tcgen05-3xtf32" or "ffma". */
+/* Which compute path the handle selected for its dims, e.g. "tcgen05-fp16x3(edge,mp,fc)" or "ffma". */
 const char* nmrgnn_compute_path(const nmrgnn_handle* h);
 
 /* Message for the last error on `h` (h == NULL: last error of a failed create). */

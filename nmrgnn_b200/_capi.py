@@ -21,7 +21,7 @@ EXPORTS = [
     "nmrgnn_abi_version", "nmrgnn_num_weights", "nmrgnn_create", "nmrgnn_destroy", "nmrgnn_forward",
     "nmrgnn_edge_features", "nmrgnn_embed", "nmrgnn_mp_layer", "nmrgnn_fc_readout", "nmrgnn_synchronize",
     "nmrgnn_kernel_launches", "nmrgnn_compute_path", "nmrgnn_last_error", "nmrgnn_knn_graph",
-    "nmrgnn_set_option", "nmrgnn_selftest_gemm",
+    "nmrgnn_set_option", "nmrgnn_selftest_gemm", "nmrgnn_stage_times",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library() -> C.CDLL:
     lib.nmrgnn_knn_graph.argtypes = [vp, fp, fp, i64, i64, i32, C.c_float, fp, fp, fp, C.c_int, vp]
     lib.nmrgnn_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.nmrgnn_selftest_gemm.argtypes = [vp, fp, fp, fp, C.c_int]
+    lib.nmrgnn_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     if lib.nmrgnn_abi_version() != 1:
         raise ImportError("libnmrgnn_b200.so ABI version mismatch")
     _lib = lib
@@ -133,6 +134,15 @@ class Handle:
 
     def set_option(self, name: str, value: int) -> None:
         self.check(self._lib.nmrgnn_set_option(self._h, name.encode(), int(value)))
+
+    def stage_times(self) -> dict:
+        """Device ms per stage of the last forward run with option "profile" = 1."""
+        buf = (C.c_float * 80)()
+        n = self._lib.nmrgnn_stage_times(self._h, buf, 80)
+        if n < 0:
+            self.check(n)
+        ms = [float(buf[i]) for i in range(n)]
+        return {"edge": ms[0], "embed": ms[1], "mp_layers": ms[2:n - 1], "fc_readout": ms[n - 1]}
 
     def synchronize(self, stream: Optional[int] = None) -> None:
         self.check(self._lib.nmrgnn_synchronize(self._h, stream))

@@ -4,6 +4,8 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -55,9 +57,17 @@ struct nmrgnn_handle {
   DevBuf pos, offs;
   // tensor-core path (F=256, H=128, E<=8): pre-split, pre-swizzled operand images
   bool tc_ok = false;
-  const uint8_t* edge_img = nullptr;    // [n_hidden][8][hi 8192 | lo 8192]
-  const uint8_t* edge_f_img = nullptr;  // [8][hi 1024 | lo 1024]
+  const uint8_t* edge_img = nullptr;    // [n_hidden][4][hi 8192 | lo 8192]   fp16 split
+  const uint8_t* edge_f_img = nullptr;  // [4][hi 1024 | lo 1024]
   const float* edge_bias = nullptr;     // [n_hidden][128]
+  float edge_in_scale[MAX_DENSE + 1];   // a-priori power-of-two range scaling per edge layer
+  float edge_out_scale[MAX_DENSE + 1];
+  bool profile = false;                 // record CUDA events around the stages of nmrgnn_forward
+  std::vector<cudaEvent_t> ev;          // [n_mp + 4] stage boundaries of the last profiled forward
+  bool ev_valid = false;
+  bool mp_tc_ok = false;                // MP layer on tensor cores (F=256, E<=3; K<=16 checked per call)
+  std::vector<const uint8_t*> mp_img;   // per layer: [8 passes][E][hi 16384 | lo 16384]
+  DevBuf rec, hmaxA, hmaxB;
 };
 
 namespace {
@@ -137,6 +147,59 @@ void pack_sw64(const float* W, int K, int ldw, int n0, int rows_valid, int rows_
         std::memcpy(out.data() + (size_t)c * 2 * tile + off, &hi, 4);
         std::memcpy(out.data() + (size_t)c * 2 * tile + tile + off, &lo, 4);
       }
+}
+
+// fp16 scaled-split B-operand images (tc_common.cuh "fp16x3").  W is [K][ldw] row-major (in -> out);
+// one 64-byte swizzled row per output feature, 32 consecutive k per chunk.
+// Layout: [chunk][hi tile | lo tile], hi = fp16(w), lo = fp16((w - hi) * 2^11).
+// `get(k, n)` returns the weight for contraction index k and output feature n.
+template <typename Get>
+void pack_sw64_f16(Get get, int K, int rows_valid, int rows_tile, std::vector<uint8_t>& out) {
+  const int chunks = K / tc::HK;
+  const size_t tile = (size_t)rows_tile * 64;
+  out.assign((size_t)chunks * 2 * tile, 0);
+  for (int c = 0; c < chunks; ++c)
+    for (int n = 0; n < rows_valid; ++n)
+      for (int kk = 0; kk < tc::HK; ++kk) {
+        const float w = get(c * tc::HK + kk, n);
+        const __half hi = __float2half_rn(w);
+        const __half lo = __float2half_rn((w - __half2float(hi)) * tc::LO_SCALE);
+        const size_t off = (size_t)n * 64 + ((((size_t)kk >> 3) ^ (((size_t)n >> 1) & 3)) << 4) + (((size_t)kk & 7) << 1);
+        std::memcpy(out.data() + (size_t)c * 2 * tile + off, &hi, 2);
+        std::memcpy(out.data() + (size_t)c * 2 * tile + tile + off, &lo, 2);
+      }
+}
+
+// upper bound of |act(x)| for |x| <= b
+float act_bound(float b, int act) {
+  switch (act) {
+    case ACT_SOFTPLUS: return b + 0.6931472f;
+    case ACT_TANH: return 1.0f;
+    default: return b;
+  }
+}
+// smallest s >= 0 with bound * 2^-s <= 2^15 (fp16 operands stay finite with 2x margin)
+int scale_exp_for(float bound) {
+  int s = 0;
+  while (bound > 32768.0f && s < 120) {
+    bound *= 0.5f;
+    ++s;
+  }
+  return s;
+}
+float max_abs(const float* w, size_t n) {
+  float m = 0.f;
+  for (size_t i = 0; i < n; ++i) m = std::fmax(m, std::fabs(w[i]));
+  return m;
+}
+// max over output features n of sum_k |W[k][n]|, W [K][N] row-major
+float max_col_abs_sum(const float* W, int K, int N) {
+  std::vector<double> s(N, 0.0);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) s[n] += std::fabs((double)W[(size_t)k * N + n]);
+  double m = 0;
+  for (double v : s) m = std::max(m, v);
+  return (float)m;
 }
 
 // float32 grid exactly as tf.linspace evaluates it for float32 inputs:
@@ -221,14 +284,19 @@ int grid_for(const nmrgnn_handle* h, int64_t tiles, int per_sm) {
 
 // ------------------------------------------------------------------ launches
 int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
-                const int32_t* nlist, int64_t n_atoms) {
+                const int32_t* nlist, int64_t n_atoms, float4* rec = nullptr) {
   if (n_edges == 0) return NMRGNN_OK;
   if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
   if (h->tc_ok && !h->force_ffma) {
     EdgeTcArgs t{};
     t.edges = edges;
     t.out = out;
+    t.rec = rec;
     t.n_edges = n_edges;
+    for (int i = 0; i <= MAX_DENSE; ++i) {
+      t.in_scale[i] = h->edge_in_scale[i];
+      t.out_scale[i] = h->edge_out_scale[i];
+    }
     t.centers = h->centers;
     t.gap = h->gap;
     t.Wimg = h->edge_img;
@@ -317,6 +385,47 @@ int launch_mp(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in, co
   return NMRGNN_OK;
 }
 
+bool mp_tc_usable(const nmrgnn_handle* h, int K) {
+  return h->tc_ok && h->mp_tc_ok && !h->force_ffma && K >= 1 && K <= MTC_KMAX;
+}
+
+int launch_absmax(nmrgnn_handle* h, cudaStream_t s, const float* nodes, int64_t n, float* hmax) {
+  if (n == 0) return NMRGNN_OK;
+  row_absmax256_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(nodes, hmax, n);
+  h->launches++;
+  return NMRGNN_OK;
+}
+
+int launch_pack_rec(nmrgnn_handle* h, cudaStream_t s, const int32_t* nlist, const float* efeat, float4* rec,
+                    int64_t n_edges, int64_t n_atoms) {
+  if (n_edges == 0) return NMRGNN_OK;
+  pack_edge_records_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, s>>>(nlist, efeat, rec, n_edges,
+                                                                              h->d.edge_features, n_atoms, h->err_flag);
+  h->launches++;
+  return NMRGNN_OK;
+}
+
+int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in, const float* hmax_in,
+                 const float4* rec, const float* invdeg, int64_t n, int K, float* h_out, float* hmax_out) {
+  if (n == 0) return NMRGNN_OK;
+  MpTcArgs a{};
+  a.h_in = h_in;
+  a.hmax_in = hmax_in;
+  a.h_out = h_out;
+  a.hmax_out = hmax_out;
+  a.rec = rec;
+  a.inv_degree = invdeg;
+  a.Wimg = h->mp_img[layer];
+  a.n_atoms = n;
+  a.K = K;
+  a.E = h->d.edge_features;
+  a.act = h->d.mp_activation;
+  const int64_t tiles = (n + 127) / 128;
+  mp_layer_tc_kernel<<<grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s>>>(a);
+  h->launches++;
+  return NMRGNN_OK;
+}
+
 int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float* atoms, int64_t n, float* peaks,
               float* fc_nodes) {
   if (n == 0) return NMRGNN_OK;
@@ -368,8 +477,9 @@ void nmrgnn_destroy(nmrgnn_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (float* p : h->owned) cudaFree(p);
   for (DevBuf* b : {&h->atoms, &h->nlist, &h->edges, &h->invdeg, &h->efeat, &h->hA, &h->hB, &h->peaks, &h->tmp_in,
-                    &h->tmp_out, &h->pos, &h->offs})
+                    &h->tmp_out, &h->pos, &h->offs, &h->rec, &h->hmaxA, &h->hmaxB})
     if (b->p) cudaFree(b->p);
+  for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->err_flag) cudaFree(h->err_flag);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -489,25 +599,62 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<3>()));
     CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<4>()));
   }
+  // tensor-core path: fp16 scaled-split operands need every weight below the fp16 range
   h->tc_ok = h->fast_path && E <= 8 && dims->n_edge_fc >= 2;
   if (h->tc_ok) {
     const int n_hidden = dims->n_edge_fc - 1;
     std::vector<uint8_t> img, all;
     std::vector<float> bias((size_t)n_hidden * 128);
     int wi = 0;
+    float bound = 1.0f;  // RBF * mask <= 1
+    h->edge_in_scale[0] = h->edge_out_scale[0] = 1.0f;
     for (int l = 0; l < n_hidden; ++l, wi += 2) {
-      pack_sw64(weights[wi], H, H, 0, H, H, img);
+      const float* W = weights[wi];
+      if (max_abs(W, (size_t)H * H) > 60000.f) h->tc_ok = false;
+      pack_sw64_f16([&](int k, int n) { return W[(size_t)k * H + n]; }, H, H, H, img);
       all.insert(all.end(), img.begin(), img.end());
       std::memcpy(bias.data() + (size_t)l * 128, weights[wi + 1], 128 * sizeof(float));
+      bound = act_bound(bound * max_col_abs_sum(W, H, H) + max_abs(weights[wi + 1], H), dims->fc_activation);
+      const int sx = scale_exp_for(bound);
+      h->edge_in_scale[l + 1] = tc::pow2f_exact(-sx);
+      h->edge_out_scale[l + 1] = tc::pow2f_exact(sx);
     }
     TRY_RC(upload_bytes(h, all.data(), all.size(), &h->edge_img));
-    pack_sw64(weights[wi], H, E, 0, E, 16, img);
+    {
+      const float* W = weights[wi];
+      if (max_abs(W, (size_t)H * E) > 60000.f) h->tc_ok = false;
+      pack_sw64_f16([&](int k, int n) { return W[(size_t)k * E + n]; }, H, E, 16, img);
+    }
     TRY_RC(upload_bytes(h, img.data(), img.size(), &h->edge_f_img));
     TRY_RC(upload(h, bias.data(), bias.size(), &h->edge_bias));
     CUDA_RC(cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ETC_SMEM));
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    CUDA_RC(cudaFuncSetAttribute(tc_selftest_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STH_SMEM));
   }
-  h->path = h->tc_ok ? "tcgen05-3xtf32(edge)+ffma" : "ffma";
+  h->mp_tc_ok = h->tc_ok && E <= 3 && dims->n_mp >= 1;
+  if (h->mp_tc_ok) {
+    const int w0 = 2 * dims->n_edge_fc + 1;
+    for (int l = 0; l < dims->n_mp; ++l)
+      if (max_abs(weights[w0 + l], (size_t)F * F * E) > 60000.f) h->mp_tc_ok = false;
+  }
+  if (h->mp_tc_ok) {
+    const int w0 = 2 * dims->n_edge_fc + 1;
+    h->mp_img.resize(dims->n_mp);
+    std::vector<uint8_t> img;
+    for (int l = 0; l < dims->n_mp; ++l) {
+      const float* src = weights[w0 + l];   // w[l_in, m, n]
+      // contraction index kg = (pass*E + n)*32 + ll  <->  input feature 32*pass + ll, edge channel n
+      pack_sw64_f16(
+          [&](int kg, int m) {
+            const int qch = kg / 32, ll = kg % 32, ps = qch / E, n = qch % E;
+            return src[((size_t)(32 * ps + ll) * F + m) * E + n];
+          },
+          F * E, F, F, img);
+      TRY_RC(upload_bytes(h, img.data(), img.size(), &h->mp_img[l]));
+    }
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MTC_SMEM));
+  }
+  h->path = h->tc_ok ? (h->mp_tc_ok ? "tcgen05-fp16x3(edge,mp)+ffma(fc)" : "tcgen05-fp16x3(edge)+ffma") : "ffma";
 #undef TRY_RC
 #undef CUDA_RC
   *out = h;
@@ -582,8 +729,18 @@ int nmrgnn_mp_layer(nmrgnn_handle* h, int32_t layer, const float* nodes_in, cons
   if ((rc = io.in(edge_features, n_atoms * k * E * sizeof(float), h->efeat, &d_ef))) return rc;
   if ((rc = io.in(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;
   if ((rc = io.out_buf(nodes_out, n_atoms * F * sizeof(float), h->hB, &d_out))) return rc;
-  if ((rc = launch_mp(h, s, layer, (const float*)d_in, (const int32_t*)d_nl, (const float*)d_ef, (const float*)d_inv,
-                      n_atoms, k, (float*)d_out)))
+  if (mp_tc_usable(h, k)) {
+    if ((rc = ensure(h, h->rec, n_atoms * k * sizeof(float4)))) return rc;
+    if ((rc = ensure(h, h->hmaxA, n_atoms * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->hmaxB, n_atoms * sizeof(float)))) return rc;
+    if ((rc = launch_pack_rec(h, s, (const int32_t*)d_nl, (const float*)d_ef, (float4*)h->rec.p, n_atoms * k, n_atoms)))
+      return rc;
+    if ((rc = launch_absmax(h, s, (const float*)d_in, n_atoms, (float*)h->hmaxA.p))) return rc;
+    if ((rc = launch_mp_tc(h, s, layer, (const float*)d_in, (const float*)h->hmaxA.p, (const float4*)h->rec.p,
+                           (const float*)d_inv, n_atoms, k, (float*)d_out, (float*)h->hmaxB.p)))
+      return rc;
+  } else if ((rc = launch_mp(h, s, layer, (const float*)d_in, (const int32_t*)d_nl, (const float*)d_ef,
+                             (const float*)d_inv, n_atoms, k, (float*)d_out)))
     return rc;
   if ((rc = io.finish(nodes_out, d_out, n_atoms * F * sizeof(float)))) return rc;
   return end_call(h, stream, s);
@@ -635,15 +792,49 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
   float* ef = (float*)h->efeat.p;
   float* ha = (float*)h->hA.p;
   float* hb = (float*)h->hB.p;
-  if ((rc = launch_edge(h, s, (const float*)d_edges, n_atoms * k, ef, (const int32_t*)d_nl, n_atoms))) return rc;
-  if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
-  for (int l = 0; l < h->d.n_mp; ++l) {
-    if ((rc = launch_mp(h, s, l, ha, (const int32_t*)d_nl, ef, (const float*)d_inv, n_atoms, k, hb))) return rc;
-    float* t = ha;
-    ha = hb;
-    hb = t;
+  if (h->profile && h->ev.empty()) {
+    h->ev.resize(h->d.n_mp + 4);
+    for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
+  }
+  int mk = 0;
+  auto mark = [&]() {
+    if (h->profile) cudaEventRecord(h->ev[mk++], s);
+  };
+  mark();
+  if (mp_tc_usable(h, k) && h->d.n_mp > 0) {
+    // tensor-core route: the edge kernel emits {e0,e1,e2,idx} records, the MP layers carry max|h| per atom
+    if ((rc = ensure(h, h->rec, n_atoms * k * sizeof(float4)))) return rc;
+    if ((rc = ensure(h, h->hmaxA, n_atoms * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->hmaxB, n_atoms * sizeof(float)))) return rc;
+    float4* rec = (float4*)h->rec.p;
+    float* ma = (float*)h->hmaxA.p;
+    float* mb = (float*)h->hmaxB.p;
+    if ((rc = launch_edge(h, s, (const float*)d_edges, n_atoms * k, nullptr, (const int32_t*)d_nl, n_atoms, rec)))
+      return rc;
+    mark();
+    if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
+    if ((rc = launch_absmax(h, s, ha, n_atoms, ma))) return rc;
+    mark();
+    for (int l = 0; l < h->d.n_mp; ++l) {
+      if ((rc = launch_mp_tc(h, s, l, ha, ma, rec, (const float*)d_inv, n_atoms, k, hb, mb))) return rc;
+      mark();
+      std::swap(ha, hb);
+      std::swap(ma, mb);
+    }
+  } else {
+    if ((rc = launch_edge(h, s, (const float*)d_edges, n_atoms * k, ef, (const int32_t*)d_nl, n_atoms))) return rc;
+    mark();
+    if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
+    mark();
+    for (int l = 0; l < h->d.n_mp; ++l) {
+      if ((rc = launch_mp(h, s, l, ha, (const int32_t*)d_nl, ef, (const float*)d_inv, n_atoms, k, hb))) return rc;
+      mark();
+      std::swap(ha, hb);
+    }
   }
   if ((rc = launch_fc(h, s, ha, (const float*)d_atoms, n_atoms, (float*)d_peaks, nullptr))) return rc;
+  mark();
+  h->ev_valid = h->profile;
   if ((rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
   return end_call(h, stream, s);
 }
@@ -653,9 +844,11 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
   int rc = begin_call(h, NMRGNN_MEM_HOST, nullptr, &s);
   if (rc) return rc;
   if (!A || !W || !D) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
+  if (mode < 0 || mode > 3) return fail(h, NMRGNN_ERR_BAD_DIMS, "mode must be 0..3");
   if (!h->tc_ok) return fail(h, NMRGNN_ERR_BAD_DIMS, "tensor-core path not available for this geometry");
   std::vector<uint8_t> img;
-  pack_sw64(W, ST_K, 128, 0, 128, 128, img);
+  if (mode <= 1) pack_sw64(W, ST_K, 128, 0, 128, 128, img);
+  else pack_sw64_f16([&](int k, int n) { return W[(size_t)k * 128 + n]; }, ST_K, 128, 128, img);
   if ((rc = ensure(h, h->tmp_in, 128 * ST_K * sizeof(float) + img.size()))) return rc;
   if ((rc = ensure(h, h->tmp_out, 128 * 128 * sizeof(float)))) return rc;
   uint8_t* d_img = (uint8_t*)h->tmp_in.p;
@@ -663,14 +856,31 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
   CUDA_TRY(h, cudaMemcpyAsync(d_img, img.data(), img.size(), cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(d_A, A, 128 * ST_K * sizeof(float), cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));  // img is a local vector
-  tc_selftest_kernel<<<1, 192, ST_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
+  if (mode <= 1) tc_selftest_kernel<<<1, 192, ST_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
+  else tc_selftest_f16_kernel<<<1, 192, STH_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
   h->launches++;
   CUDA_TRY(h, cudaMemcpyAsync(D, h->tmp_out.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, s));
   return end_call(h, nullptr, s);
 }
 
+int nmrgnn_stage_times(nmrgnn_handle* h, float* ms, int cap) {
+  if (!h || !ms) return NMRGNN_ERR_BAD_DIMS;
+  if (!h->ev_valid) return fail(h, NMRGNN_ERR_BAD_DIMS, "no profiled forward recorded (set option \"profile\" = 1 first)");
+  const int n = (int)h->ev.size() - 1;
+  if (cap < n) return fail(h, NMRGNN_ERR_BAD_DIMS, "need room for %d stage times", n);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaEventSynchronize(h->ev[n]));
+  for (int i = 0; i < n; ++i) CUDA_TRY(h, cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  return n;
+}
+
 int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   if (!h || !name) return NMRGNN_ERR_BAD_DIMS;
+  if (std::strcmp(name, "profile") == 0) {
+    h->profile = value != 0;
+    h->ev_valid = false;
+    return NMRGNN_OK;
+  }
   if (std::strcmp(name, "force_ffma") == 0) {
     h->force_ffma = value != 0;
     return NMRGNN_OK;

@@ -1,7 +1,9 @@
-// Tensor-core (tcgen05, kind::tf32, 3xTF32 split) kernels of the GNN forward, sm_100a.
-// Accumulators live in tensor memory; operands are K-major 64-byte-swizzled tiles in
-// shared memory: activations are written there by the epilogue/producer warps, weights
-// arrive pre-split and pre-swizzled from global memory through 1-D bulk async copies.
+// Tensor-core (tcgen05) kernels of the GNN forward, sm_100a.
+// Production scheme: FP16 scaled-split products (tc_common.cuh, "fp16x3") with separate
+// main / correction accumulators in tensor memory; operands are K-major 64-byte-swizzled
+// tiles in shared memory: activations are written there by the producer / epilogue warps,
+// weights arrive pre-split and pre-swizzled from global memory through 1-D bulk async
+// copies (UBLKCP) into mbarrier-guarded rings.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -9,9 +11,11 @@
 namespace nmr {
 
 // ----------------------------------------------------------------------------------
-// Self-test: D[128 x 128] = A[128 x 64] * W[64 x 128] on one CTA.  mode 0: 3xTF32,
-// mode 1: hi*hi only (1xTF32).  Exercises descriptors, swizzle, TMEM addressing and
-// the bulk-copy / commit barriers in isolation.
+// Self-tests: D[128 x 128] = A[128 x 64] * W[64 x 128] on one CTA.
+//   tc_selftest_kernel      kind::tf32; mode 0: 3xTF32 (single accumulator), mode 1: 1xTF32
+//   tc_selftest_f16_kernel  kind::f16;  mode 2: fp16x3 (main + corr accumulators), mode 3: hi*hi
+// They exercise descriptors, swizzle, TMEM addressing and the bulk-copy / commit barriers
+// in isolation, and measure the accumulation behaviour of the tensor core.
 // ----------------------------------------------------------------------------------
 constexpr int ST_K = 64;
 constexpr int ST_CHUNKS = ST_K / tc::BK;
@@ -97,223 +101,685 @@ __global__ void __launch_bounds__(192, 1) tc_selftest_kernel(const float* __rest
   if (warp == 4) tc::tmem_dealloc<128>(tmem_base);
 }
 
+constexpr int STH_CHUNKS = ST_K / tc::HK;   // 2
+constexpr size_t STH_SMEM = 1024 + (size_t)STH_CHUNKS * (8192 * 2 + 16384) + 256;
+
+__global__ void __launch_bounds__(192, 1) tc_selftest_f16_kernel(const float* __restrict__ A,
+                                                                 const uint8_t* __restrict__ Bimg,
+                                                                 float* __restrict__ D, int mode) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_hi = smem;                                  // [chunks][128 rows x 64 B]
+  uint8_t* a_lo = a_hi + STH_CHUNKS * 8192;
+  uint8_t* b = a_lo + STH_CHUNKS * 8192;                 // [chunks][hi 8192 | lo 8192]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b + STH_CHUNKS * 16384);
+  uint64_t* b_full = bars;
+  uint64_t* d_full = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tc::mbar_init(b_full, 1);
+    tc::mbar_init(d_full, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tc::tmem_alloc<256>(tmem_slot);
+  __syncthreads();
+  if (warp == 5 && lane == 0) {
+    tc::mbar_expect_tx(b_full, STH_CHUNKS * 16384);
+    for (int c = 0; c < STH_CHUNKS; ++c) tc::bulk_g2s(b + c * 16384, Bimg + (size_t)c * 16384, 16384, b_full);
+  }
+  if (tid < 128) {
+    const int r = tid;
+    for (int c = 0; c < STH_CHUNKS; ++c) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x[8];
+        const float4 x0 = *reinterpret_cast<const float4*>(A + r * ST_K + c * tc::HK + j * 8);
+        const float4 x1 = *reinterpret_cast<const float4*>(A + r * ST_K + c * tc::HK + j * 8 + 4);
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
+        x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        uint4 hi, lo;
+        tc::split8_f16(x, hi, lo);
+        const uint32_t off = c * 8192 + tc::sw64_chunk_offset(r, j);
+        *reinterpret_cast<uint4*>(a_hi + off) = hi;
+        *reinterpret_cast<uint4*>(a_lo + off) = lo;
+      }
+    }
+    tc::fence_proxy_async();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t d_main = tmem_base, d_corr = tmem_base + 128;
+  if (warp == 4 && lane == 0) {
+    tc::mbar_wait(b_full, 0);
+    tc::tc_fence_after();
+    const uint32_t idesc = tc::make_idesc_f16(128, 128);
+    for (int c = 0; c < STH_CHUNKS; ++c) {
+      const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(a_hi + c * 8192));
+      const uint64_t al = tc::make_desc_sw64(tc::smem_u32(a_lo + c * 8192));
+      const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(b + c * 16384));
+      const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(b + c * 16384 + 8192));
+#pragma unroll
+      for (int ks = 0; ks < tc::HK / tc::UMMA_K_F16; ++ks) {
+        const uint64_t adv = (uint64_t)(ks * tc::UMMA_K_F16 * 2) >> 4;
+        tc::umma_f16(d_main, ah + adv, bh + adv, idesc, (c | ks) != 0);
+        if (mode == 2) {
+          tc::umma_f16(d_corr, al + adv, bh + adv, idesc, (c | ks) != 0);
+          tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+        }
+      }
+    }
+    tc::umma_commit(d_full);
+  }
+  if (tid < 128) {
+    tc::mbar_wait(d_full, 0);
+    tc::tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < 8; ++c) {
+      float v[16];
+      if (mode == 2) tc::tmem_ld16_combined(lane_base + c * 16, lane_base + 128 + c * 16, v);
+      else tc::tmem_ld16(lane_base + c * 16, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) D[tid * 128 + c * 16 + i] = v[i];
+    }
+    tc::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc<256>(tmem_base);
+}
+
 // ----------------------------------------------------------------------------------
-// Edge MLP on tensor cores.  One CTA = 128 edges per tile (persistent over tiles).
-//   warps 0-3 : thread r owns edge r: RBF prologue, then per layer the epilogue
-//               (TMEM -> +bias -> softplus -> hi/lo split -> next layer's A operand in smem)
-//   warp 4    : MMA issuer (one lane): D[128 x 128] (+)= X_chunk * W_chunk^T, 3 products
-//   warp 5    : weight loader (one lane): 16 KB bulk copies into a 4-slot ring
-// The activation operand X (hi and lo, 8 chunks of 16 features) is resident and updated
-// in place chunk by chunk; the MMA of layer l+1 starts on chunk c as soon as the epilogue
-// of layer l has produced it, while the two TMEM accumulators ping-pong between layers.
-// The last (linear, 128 -> E) layer is one more MMA with N = 16 (E padded).
+// Edge MLP on tensor cores (RBF -> EdgeFCBlock -> mask; model.py:251-261).
+// One CTA keeps TWO 128-edge tiles in flight (slots 0/1) so that the CUDA-core epilogue
+// of one tile (bias, softplus, split -> next layer's A operand) overlaps the MMAs of the
+// other.  Per slot: X (activation operand, hi+lo, 4 K-chunks of 32) in shared memory,
+// main/corr accumulators (2 x 128 columns) in tensor memory.
+//   warp 0       : weight loader (one lane): 16 KB bulk copies into a 4-slot ring
+//   warp 1       : MMA issuer (one lane) + TMEM owner
+//   warps 2..9   : epilogue group of slot 0;  warps 10..17: slot 1.  Within a group,
+//                  warp%4 selects the TMEM lane quarter (32 edges) and the warp's rank in
+//                  its quarter selects a 64-column half: thread = (edge row, 64 features).
+// The last (linear, 128 -> E) layer is one more MMA with N = 16 (E padded) against the
+// resident final-layer weights.
 // ----------------------------------------------------------------------------------
 struct EdgeTcArgs {
   const float* edges;        // [n_edges]
-  float* out;                // [n_edges, E]
+  float* out;                // optional [n_edges, E]
+  float4* rec;               // optional [n_edges] {e0, e1, e2, bits(idx)} records for the MP kernel (E <= 3)
   int64_t n_edges;
   const float* centers;      // [128]
   float gap;
-  const uint8_t* Wimg;       // hidden layers: [n_hidden][8 chunks][hi 8192 | lo 8192]
-  const uint8_t* Wfimg;      // final layer:   [8 chunks][hi 1024 | lo 1024]   (16 rows, rows >= E are zero)
+  const uint8_t* Wimg;       // hidden layers: [n_hidden][4 chunks][hi 8192 | lo 8192]
+  const uint8_t* Wfimg;      // final layer:   [4 chunks][hi 1024 | lo 1024]   (16 rows, rows >= E are zero)
   const float* bias;         // [n_hidden][128]
   const float* bias_f;       // [E]
+  float in_scale[MAX_DENSE + 1];   // power of two applied to the INPUT of layer l (a-priori range bound)
+  float out_scale[MAX_DENSE + 1];  // its inverse, applied to the accumulator of layer l
   int n_hidden;              // hidden (activated) layers, >= 1
   int E;
   int act;
-  const int32_t* nlist;      // optional validation
+  const int32_t* nlist;      // optional [n_edges]: validated against n_atoms (and packed into rec)
   int64_t n_atoms;
   int* err_flag;
 };
 
-constexpr int ETC_THREADS = 192;
-constexpr int ETC_SLOTS = 4;
-constexpr int ETC_CHUNKS = 8;          // 128 / 16
-constexpr size_t ETC_SMEM = 1024 + 2 * 65536 + ETC_SLOTS * 16384 + ETC_CHUNKS * 2048 + (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
+constexpr int ETC_THREADS = 576;
+constexpr int ETC_RING = 4;
+constexpr int ETC_CHUNKS = 4;          // 128 / 32
+constexpr int ETC_X_BYTES = ETC_CHUNKS * 16384;
+static_assert(true, "");
+constexpr size_t ETC_SMEM = 1024 + 2 * ETC_X_BYTES + ETC_RING * 16384 + ETC_CHUNKS * 2048 +
+                            (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
 
 __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* x_hi = smem;                                   // [8][8192]
-  uint8_t* x_lo = x_hi + 65536;
-  uint8_t* ring = x_lo + 65536;                           // [SLOTS][hi 8192 | lo 8192]
-  uint8_t* wf = ring + ETC_SLOTS * 16384;                 // [8][hi 1024 | lo 1024]
+  uint8_t* xs = smem;                                     // [2 slots][4 chunks][hi 8192 | lo 8192]
+  uint8_t* ring = xs + 2 * ETC_X_BYTES;                   // [RING][hi 8192 | lo 8192]
+  uint8_t* wf = ring + ETC_RING * 16384;                  // [4][hi 1024 | lo 1024]
   float* bias_s = reinterpret_cast<float*>(wf + ETC_CHUNKS * 2048);   // [n_hidden][128]
   float* cen_s = bias_s + MAX_DENSE * 128;                // [128]
   float* bf_s = cen_s + 128;                              // [16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bf_s + 16);
-  uint64_t* w_full = bars;                                // [SLOTS]
-  uint64_t* w_empty = w_full + ETC_SLOTS;                 // [SLOTS]
-  uint64_t* x_ready = w_empty + ETC_SLOTS;                // [8]
-  uint64_t* d_full = x_ready + ETC_CHUNKS;                // [2]
-  uint64_t* df_full = d_full + 2;
-  uint64_t* wf_full = df_full + 1;
+  uint64_t* w_full = bars;                                // [RING]
+  uint64_t* w_empty = w_full + ETC_RING;                  // [RING]
+  uint64_t* x_full = w_empty + ETC_RING;                  // [2]
+  uint64_t* d_full = x_full + 2;                          // [2]
+  uint64_t* wf_full = d_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wf_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < ETC_SLOTS; ++i) {
+    for (int i = 0; i < ETC_RING; ++i) {
       tc::mbar_init(&w_full[i], 1);
       tc::mbar_init(&w_empty[i], 1);
     }
-    for (int i = 0; i < ETC_CHUNKS; ++i) tc::mbar_init(&x_ready[i], 4);
-    tc::mbar_init(&d_full[0], 1);
-    tc::mbar_init(&d_full[1], 1);
-    tc::mbar_init(df_full, 1);
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(&x_full[g], 8);
+      tc::mbar_init(&d_full[g], 1);
+    }
     tc::mbar_init(wf_full, 1);
     tc::mbar_fence_init();
   }
   for (int i = tid; i < p.n_hidden * 128; i += ETC_THREADS) bias_s[i] = p.bias[i];
   for (int i = tid; i < 128; i += ETC_THREADS) cen_s[i] = p.centers[i];
   if (tid < 16) bf_s[tid] = tid < p.E ? p.bias_f[tid] : 0.0f;
-  if (warp == 4) tc::tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int64_t n_tiles = (p.n_edges + 127) / 128;
   const int n_hidden = p.n_hidden;
+  // tiles of this CTA: blockIdx.x + n * gridDim.x, n = 0 .. n_my-1; tile n lives in slot n & 1
+  const int n_my = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
-  if (warp == 5) {
+  if (warp == 0) {
     // ===================== weight loader =====================
-    if (lane == 0) {
+    if (lane == 0 && n_my > 0) {
       tc::mbar_expect_tx(wf_full, ETC_CHUNKS * 2048);
       tc::bulk_g2s(wf, p.Wfimg, ETC_CHUNKS * 2048, wf_full);
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int pair = 0; pair * 2 < n_my; ++pair)
         for (int l = 0; l < n_hidden; ++l)
-          for (int c = 0; c < ETC_CHUNKS; ++c, ++it) {
-            const uint32_t slot = it % ETC_SLOTS, ph = (it / ETC_SLOTS) & 1;
-            tc::mbar_wait(&w_empty[slot], ph ^ 1);
-            tc::mbar_expect_tx(&w_full[slot], 16384);
-            tc::bulk_g2s(ring + slot * 16384, p.Wimg + ((size_t)l * ETC_CHUNKS + c) * 16384, 16384, &w_full[slot]);
+          for (int g = 0; g < 2; ++g) {
+            if (pair * 2 + g >= n_my) continue;
+            for (int c = 0; c < ETC_CHUNKS; ++c, ++it) {
+              const uint32_t slot = it % ETC_RING, ph = (it / ETC_RING) & 1;
+              tc::mbar_wait(&w_empty[slot], ph ^ 1);
+              tc::mbar_expect_tx(&w_full[slot], 16384);
+              tc::bulk_g2s(ring + slot * 16384, p.Wimg + ((size_t)l * ETC_CHUNKS + c) * 16384, 16384, &w_full[slot]);
+            }
           }
     }
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_h = tc::make_idesc_tf32(128, 128);
-      const uint32_t idesc_f = tc::make_idesc_tf32(128, 16);
+    if (lane == 0 && n_my > 0) {
+      const uint32_t idesc_h = tc::make_idesc_f16(128, 128);
+      const uint32_t idesc_f = tc::make_idesc_f16(128, 16);
       tc::mbar_wait(wf_full, 0);
-      uint32_t it = 0, pass = 0;   // every (tile, layer) pass completes one phase of each x_ready[c]
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int l = 0; l <= n_hidden; ++l, ++pass) {
-          const bool fin = (l == n_hidden);
-          const uint32_t d_tmem = tmem_base + (fin ? 256u : (uint32_t)(l & 1) * 128u);
-          for (int c = 0; c < ETC_CHUNKS; ++c) {
-            tc::mbar_wait(&x_ready[c], pass & 1);
-            uint64_t bh, bl;
-            uint32_t slot = 0;
-            if (!fin) {
-              slot = it % ETC_SLOTS;
-              tc::mbar_wait(&w_full[slot], (it / ETC_SLOTS) & 1);
-              bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
-              bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
-            } else {
-              bh = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048));
-              bl = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048 + 1024));
-            }
+      uint32_t it = 0, px[2] = {0, 0};
+      for (int pair = 0; pair * 2 < n_my; ++pair)
+        for (int l = 0; l <= n_hidden; ++l)
+          for (int g = 0; g < 2; ++g) {
+            if (pair * 2 + g >= n_my) continue;
+            const bool fin = (l == n_hidden);
+            const uint32_t d_main = tmem_base + (uint32_t)g * 256u, d_corr = d_main + 128u;
+            tc::mbar_wait(&x_full[g], px[g]);
+            px[g] ^= 1;
             tc::tc_fence_after();
-            const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(x_hi + c * 8192));
-            const uint64_t al = tc::make_desc_sw64(tc::smem_u32(x_lo + c * 8192));
-            const uint32_t idesc = fin ? idesc_f : idesc_h;
+            for (int c = 0; c < ETC_CHUNKS; ++c) {
+              uint64_t bh, bl;
+              uint32_t slot = 0;
+              if (!fin) {
+                slot = it % ETC_RING;
+                tc::mbar_wait(&w_full[slot], (it / ETC_RING) & 1);
+                tc::tc_fence_after();
+                bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
+                bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
+              } else {
+                bh = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048));
+                bl = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048 + 1024));
+              }
+              const uint8_t* xc = xs + g * ETC_X_BYTES + c * 16384;
+              const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(xc));
+              const uint64_t al = tc::make_desc_sw64(tc::smem_u32(xc + 8192));
+              const uint32_t idesc = fin ? idesc_f : idesc_h;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * 2);
-              tc::umma_tf32(d_tmem, ah + adv, bh + adv, idesc, (c | ks) != 0);
-              tc::umma_tf32(d_tmem, al + adv, bh + adv, idesc, 1);
-              tc::umma_tf32(d_tmem, ah + adv, bl + adv, idesc, 1);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                tc::umma_f16(d_main, ah + adv, bh + adv, idesc, (c | ks) != 0);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, (c | ks) != 0);
+                tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+              }
+              if (!fin) {
+                tc::umma_commit(&w_empty[slot]);
+                ++it;
+              }
             }
-            if (!fin) {
-              tc::umma_commit(&w_empty[slot]);
-              ++it;
-            }
+            tc::umma_commit(&d_full[g]);
           }
-          tc::umma_commit(fin ? df_full : &d_full[l & 1]);
-        }
-      }
     }
   } else {
-    // ===================== producer / epilogue warps (thread r = edge r) =====================
-    const int r = tid;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t ph_d[2] = {0, 0}, ph_f = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int64_t e = tile * 128 + r;
+    // ===================== epilogue groups: thread = (edge row, 64 features) =====================
+    const int we = warp - 2;
+    const int g = we >> 3;
+    const int q = warp & 3;
+    const int half = (we & 7) >> 2;
+    const int row = q * 32 + lane;
+    const int col0 = half * 64;
+    uint8_t* xg = xs + g * ETC_X_BYTES;
+    const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+    const uint32_t t_corr = t_main + 128u;
+    uint32_t pd = 0;
+    for (int n = g; n < n_my; n += 2) {
+      const int64_t tile = blockIdx.x + (int64_t)n * gridDim.x;
+      const int64_t e = tile * 128 + row;
       float d = 0.0f;
+      int32_t idx = 0;
       if (e < p.n_edges) {
         d = p.edges[e];
-        if (p.nlist != nullptr) {
-          const int32_t idx = p.nlist[e];
-          if (idx < 0 || idx >= p.n_atoms) atomicOr(p.err_flag, 1);
+        if (p.nlist != nullptr && half == 0) {
+          idx = p.nlist[e];
+          if (idx < 0 || idx >= p.n_atoms) {
+            atomicOr(p.err_flag, 1);
+            idx = 0;
+          }
         }
       }
       const bool m = d > 0.0f;
       // pass 0: RBF expansion * mask  (layers.py:137-140, model.py:251-257)
-      for (int c = 0; c < ETC_CHUNKS; ++c) {
+      {
+        const float s_in = p.in_scale[0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 x;
-          float* xv = reinterpret_cast<float*>(&x);
+        for (int cc = 0; cc < 4; ++cc) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float diff = d - cen_s[c * 16 + j * 4 + i];
-            const float v = expf(__fdiv_rn(-__fmul_rn(diff, diff), p.gap));
-            xv[i] = m ? v : 0.0f;
+          for (int hh = 0; hh < 2; ++hh) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float diff = d - cen_s[col0 + cc * 16 + hh * 8 + i];
+              const float v = expf(__fdiv_rn(-__fmul_rn(diff, diff), p.gap));
+              x[i] = m ? v * s_in : 0.0f;
+            }
+            uint4 hi, lo;
+            tc::split8_f16(x, hi, lo);
+            const uint32_t off = (uint32_t)(half * 2 + (cc >> 1)) * 16384u + tc::sw64_chunk_offset(row, (cc & 1) * 2 + hh);
+            *reinterpret_cast<uint4*>(xg + off) = hi;
+            *reinterpret_cast<uint4*>(xg + off + 8192) = lo;
           }
-          float4 hi, lo;
-          tc::split4(x, hi, lo);
-          const uint32_t off = c * 8192 + tc::sw64_chunk_offset(r, j);
-          *reinterpret_cast<float4*>(x_hi + off) = hi;
-          *reinterpret_cast<float4*>(x_lo + off) = lo;
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&x_ready[c]);
+        if (lane == 0) tc::mbar_arrive(&x_full[g]);
       }
-      // hidden layers: X <- act(D + b), in place, chunk by chunk
+      // hidden layers: X <- act(D * 2^s + b) * 2^-s', in place
       for (int l = 0; l < n_hidden; ++l) {
-        tc::mbar_wait(&d_full[l & 1], ph_d[l & 1]);
-        ph_d[l & 1] ^= 1;
+        tc::mbar_wait(&d_full[g], pd);
+        pd ^= 1;
         tc::tc_fence_after();
-        const float* bl = bias_s + l * 128;
-        for (int c = 0; c < ETC_CHUNKS; ++c) {
+        const float* bl = bias_s + l * 128 + col0;
+        const float s_out = p.out_scale[l], s_in = p.in_scale[l + 1];
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
           float v[16];
-          tc::tmem_ld16(lane_base + (uint32_t)(l & 1) * 128u + c * 16, v);
+          tc::tmem_ld16_combined(t_main + col0 + cc * 16, t_corr + col0 + cc * 16, v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 x;
-            x.x = apply_act(v[j * 4 + 0] + bl[c * 16 + j * 4 + 0], p.act);
-            x.y = apply_act(v[j * 4 + 1] + bl[c * 16 + j * 4 + 1], p.act);
-            x.z = apply_act(v[j * 4 + 2] + bl[c * 16 + j * 4 + 2], p.act);
-            x.w = apply_act(v[j * 4 + 3] + bl[c * 16 + j * 4 + 3], p.act);
-            float4 hi, lo;
-            tc::split4(x, hi, lo);
-            const uint32_t off = c * 8192 + tc::sw64_chunk_offset(r, j);
-            *reinterpret_cast<float4*>(x_hi + off) = hi;
-            *reinterpret_cast<float4*>(x_lo + off) = lo;
+          for (int hh = 0; hh < 2; ++hh) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              x[i] = apply_act(fmaf(v[hh * 8 + i], s_out, bl[cc * 16 + hh * 8 + i]), p.act) * s_in;
+            uint4 hi, lo;
+            tc::split8_f16(x, hi, lo);
+            const uint32_t off = (uint32_t)(half * 2 + (cc >> 1)) * 16384u + tc::sw64_chunk_offset(row, (cc & 1) * 2 + hh);
+            *reinterpret_cast<uint4*>(xg + off) = hi;
+            *reinterpret_cast<uint4*>(xg + off + 8192) = lo;
           }
-          tc::fence_proxy_async();
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&x_ready[c]);
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_full[g]);
+      }
+      // final linear layer (columns 0..15 of the slot's accumulators) * mask
+      tc::mbar_wait(&d_full[g], pd);
+      pd ^= 1;
+      tc::tc_fence_after();
+      if (half == 0) {
+        float va[8], vb[8];
+        tc::tmem_ld8(t_main, va);
+        tc::tmem_ld8(t_corr, vb);
+        if (e < p.n_edges) {
+          const float s_out = p.out_scale[n_hidden];
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
+          if (p.out != nullptr)
+            for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
+          if (p.rec != nullptr) p.rec[e] = make_float4(o[0], o[1], o[2], __int_as_float(idx));
         }
       }
-      // final linear layer (already in TMEM columns 256..271) * mask
-      tc::mbar_wait(df_full, ph_f);
-      ph_f ^= 1;
-      tc::tc_fence_after();
-      float v[8];
-      tc::tmem_ld8(lane_base + 256u, v);
       tc::tc_fence_before();
-      if (e < p.n_edges) {
-        for (int n = 0; n < p.E; ++n) p.out[e * p.E + n] = m ? v[n] + bf_s[n] : 0.0f;
-      }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace nmr
+
+namespace nmr {
+
+// ----------------------------------------------------------------------------------
+// Helpers for the tensor-core MP layer: edge records and per-atom feature maxima.
+// ----------------------------------------------------------------------------------
+// rec[e] = {e0, e1, e2, bits(idx)} from separate nlist / edge-feature arrays (E <= 3);
+// out-of-range indices are flagged and replaced by 0 (the call then fails with BAD_INDEX).
+__global__ void __launch_bounds__(256) pack_edge_records_kernel(const int32_t* __restrict__ nlist,
+                                                                const float* __restrict__ efeat, float4* __restrict__ rec,
+                                                                int64_t n_edges, int E, int64_t n_atoms, int* err_flag) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n_edges) return;
+  int32_t idx = nlist[e];
+  if (idx < 0 || idx >= n_atoms) {
+    atomicOr(err_flag, 1);
+    idx = 0;
+  }
+  float4 r = make_float4(0.f, 0.f, 0.f, __int_as_float(idx));
+  r.x = efeat[e * E];
+  if (E > 1) r.y = efeat[e * E + 1];
+  if (E > 2) r.z = efeat[e * E + 2];
+  rec[e] = r;
+}
+
+// hmax[i] = max_l |h[i, l]|, F = 256: one warp per atom
+__global__ void __launch_bounds__(256) row_absmax256_kernel(const float* __restrict__ h, float* __restrict__ hmax,
+                                                            int64_t n_atoms) {
+  const int64_t atom = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (atom >= n_atoms) return;
+  const int lane = threadIdx.x & 31;
+  const float4 a = *reinterpret_cast<const float4*>(h + atom * 256 + lane * 4);
+  const float4 b = *reinterpret_cast<const float4*>(h + atom * 256 + 128 + lane * 4);
+  float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                  fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w))));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) hmax[atom] = m;
+}
+
+// ----------------------------------------------------------------------------------
+// MP layer on tensor cores, F = 256, E <= 3, K <= 16 (layers.py:26-46 + model.py:167).
+// One CTA = 128 atoms per tile, persistent over tiles.
+//   T[i,(p,n,ll)] = sum_j e[i,j,n] * h[nl[i,j], 32p+ll]     gather-aggregate, fp32 FFMA (producers)
+//   D[i, m]       = sum_k T[i,k] * W'[k, m]                 tcgen05 fp16x3, K = 256*E, N = 256
+//   h_out[i, m]   = act(inv_degree[i] * D[i,m]) + h_in[i,m] epilogue
+// The producers build T pass by pass (one pass = 32 input features x E = E operand chunks of
+// 32 k), scale each row by a power of two from an a-priori bound (fp16 range), split it into
+// the hi/lo operand tiles and hand it to the MMA warp through a 2-pass ring; W' streams
+// through a 3-slot ring of 32 KB bulk copies.  T never reaches HBM.
+//   warp 0: W' loader   warp 1: MMA issuer + TMEM owner   warp 2: edge-record loader
+//   warps 4-7: epilogue (thread = atom row)                warps 8-15: producers
+// ----------------------------------------------------------------------------------
+struct MpTcArgs {
+  const float* h_in;         // [n_atoms, 256]
+  const float* hmax_in;      // [n_atoms]  max_l |h_in[i,l]|
+  float* h_out;              // [n_atoms, 256]
+  float* hmax_out;           // [n_atoms]
+  const float4* rec;         // [n_atoms * K] {e0, e1, e2, bits(idx)}
+  const float* inv_degree;   // [n_atoms]
+  const uint8_t* Wimg;       // [8 passes][E][hi 16384 | lo 16384]
+  int64_t n_atoms;
+  int K;
+  int E;
+  int act;
+};
+
+constexpr int MTC_THREADS = 512;
+constexpr int MTC_PASSES = 8;          // 256 / 32
+constexpr int MTC_BRING = 3;
+constexpr int MTC_KMAX = 16;
+// 64-byte-swizzled tiles need a 512-byte aligned base
+constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * 32768 + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
+static_assert(MTC_SMEM <= 227 * 1024, "MP tensor-core kernel exceeds the 227 KB shared-memory limit");
+
+__global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~uintptr_t(511));
+  uint8_t* a_st = smem;                                   // [2 stages][3 chunks][hi 8192 | lo 8192]
+  uint8_t* b_ring = a_st + 2 * 3 * 16384;                 // [BRING][hi 16384 | lo 16384]
+  float4* rec_s = reinterpret_cast<float4*>(b_ring + MTC_BRING * 32768);   // [128 * K]
+  float* fscale = reinterpret_cast<float*>(rec_s + 128 * MTC_KMAX);        // [2][128]  2^-s
+  float* oscale = fscale + 2 * 128;                                         // [2][128]  2^s * inv_degree
+  uint64_t* bars = reinterpret_cast<uint64_t*>(oscale + 2 * 128);
+  uint64_t* a_full = bars;            // [2]
+  uint64_t* a_empty = a_full + 2;     // [2]
+  uint64_t* b_full = a_empty + 2;     // [BRING]
+  uint64_t* b_empty = b_full + MTC_BRING;
+  uint64_t* rec_full = b_empty + MTC_BRING;
+  uint64_t* rec_empty = rec_full + 1;
+  uint64_t* d_full = rec_empty + 1;
+  uint64_t* d_empty = d_full + 1;
+  uint64_t* sc_full = d_empty + 1;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc_full + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&a_full[i], 8);
+      tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&sc_full[i], 8);
+    }
+    for (int i = 0; i < MTC_BRING; ++i) {
+      tc::mbar_init(&b_full[i], 1);
+      tc::mbar_init(&b_empty[i], 1);
+    }
+    tc::mbar_init(rec_full, 1);
+    tc::mbar_init(rec_empty, 8);
+    tc::mbar_init(d_full, 1);
+    tc::mbar_init(d_empty, 4);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int K = p.K, E = p.E;
+  const int64_t n_tiles = (p.n_atoms + 127) / 128;
+
+  if (warp == 0) {
+    // ===================== W' loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int q = 0; q < MTC_PASSES * E; ++q, ++it) {
+          const uint32_t slot = it % MTC_BRING, ph = (it / MTC_BRING) & 1;
+          tc::mbar_wait(&b_empty[slot], ph ^ 1);
+          tc::mbar_expect_tx(&b_full[slot], 32768);
+          tc::bulk_g2s(b_ring + slot * 32768, p.Wimg + (size_t)q * 32768, 32768, &b_full[slot]);
+        }
+    }
+  } else if (warp == 2) {
+    // ===================== edge-record loader =====================
+    if (lane == 0) {
+      uint32_t t = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        const int64_t a0 = tile * 128;
+        const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 16u;
+        tc::mbar_wait(rec_empty, (t & 1) ^ 1);
+        tc::mbar_expect_tx(rec_full, bytes);
+        tc::bulk_g2s(rec_s, p.rec + a0 * K, bytes, rec_full);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(128, 256);
+      const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
+      uint32_t it = 0, pass = 0, t = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        tc::mbar_wait(d_empty, (t & 1) ^ 1);      // epilogue has drained the previous tile's accumulators
+        tc::tc_fence_after();
+        for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
+          const uint32_t st = pass & 1;
+          tc::mbar_wait(&a_full[st], (pass >> 1) & 1);
+          tc::tc_fence_after();
+          for (int n = 0; n < E; ++n, ++it) {
+            const uint32_t slot = it % MTC_BRING;
+            tc::mbar_wait(&b_full[slot], (it / MTC_BRING) & 1);
+            tc::tc_fence_after();
+            const uint8_t* ac = a_st + (st * 3 + n) * 16384;
+            const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(ac));
+            const uint64_t al = tc::make_desc_sw64(tc::smem_u32(ac + 8192));
+            const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * 32768));
+            const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * 32768 + 16384));
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              const uint32_t acc = (ps | n | ks) != 0;
+              tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
+              tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc);
+              tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+            }
+            tc::umma_commit(&b_empty[slot]);
+          }
+          tc::umma_commit(&a_empty[st]);
+        }
+        tc::umma_commit(d_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue: thread = atom row =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_corr = t_main + 256u;
+    uint32_t t = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int64_t a0 = tile * 128;
+      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      const bool valid = row < rows;
+      const int64_t atom = a0 + row;
+      tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
+      const float osc = oscale[(t & 1) * 128 + row];
+      tc::mbar_wait(d_full, t & 1);
+      tc::tc_fence_after();
+      const float* hin = p.h_in + atom * 256;
+      float* hout = p.h_out + atom * 256;
+      float hm = 0.0f;
+#pragma unroll 1
+      for (int cc = 0; cc < 16; ++cc) {
+        float v[16];
+        tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 r = *reinterpret_cast<const float4*>(hin + cc * 16 + j * 4);
+            float4 o;
+            o.x = apply_act(v[j * 4 + 0] * osc, p.act) + r.x;
+            o.y = apply_act(v[j * 4 + 1] * osc, p.act) + r.y;
+            o.z = apply_act(v[j * 4 + 2] * osc, p.act) + r.z;
+            o.w = apply_act(v[j * 4 + 3] * osc, p.act) + r.w;
+            hm = fmaxf(hm, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            *reinterpret_cast<float4*>(hout + cc * 16 + j * 4) = o;
+          }
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(d_empty);
+      if (valid) p.hmax_out[atom] = hm;
+    }
+  } else if (warp >= 8) {
+    // ===================== producers: gather-aggregate, scale, split =====================
+    const int pw = warp - 8;                 // 0..7
+    const int ptid = tid - 256;              // 0..255
+    const int q8 = lane & 7;                 // 4-feature group inside the 32-feature pass
+    const int rsub = lane >> 3;              // row inside the warp's 4-row group
+    uint32_t pass = 0, t = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const int64_t a0 = tile * 128;
+      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      float* fs = fscale + (t & 1) * 128;
+      float* os = oscale + (t & 1) * 128;
+      tc::mbar_wait(rec_full, t & 1);
+      // per-row bound |T[i,.]| <= sum_j max_n|e_ijn| * hmax[nl_ij]  ->  power-of-two scale
+      {
+        const int row = ptid >> 1, hf = ptid & 1;
+        float b = 0.0f;
+        if (row < rows) {
+          for (int j = hf; j < K; j += 2) {
+            const float4 r = rec_s[row * K + j];
+            const float em = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fabsf(r.z));
+            if (em != 0.0f) b = fmaf(em, __ldg(p.hmax_in + __float_as_int(r.w)), b);
+          }
+        }
+        b += __shfl_xor_sync(0xffffffffu, b, 1);
+        if (hf == 0) {
+          // exponent of b (0 for b < 2^15): scale so that |T| * 2^-s < 2^15
+          int s = ((__float_as_int(b) >> 23) & 0xff) - 127 - 14;
+          s = b > 0.0f ? max(s, 0) : 0;
+          s = min(s, 100);
+          fs[row] = tc::pow2f_exact(-s);
+          os[row] = row < rows ? tc::pow2f_exact(s) * p.inv_degree[a0 + row] : 0.0f;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (lane == 0) tc::mbar_arrive(&sc_full[t & 1]);
+      for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
+        const uint32_t st = pass & 1;
+        tc::mbar_wait(&a_empty[st], ((pass >> 1) & 1) ^ 1);
+        uint8_t* ab = a_st + st * 3 * 16384;
+        const float* hcol = p.h_in + ps * 32 + q8 * 4;
+#pragma unroll 1
+        for (int step = 0; step < 4; ++step) {
+          const int row = step * 32 + pw * 4 + rsub;
+          float acc[3][4];
+#pragma unroll
+          for (int n = 0; n < 3; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
+          if (row < rows) {
+            const float4* rr = rec_s + row * K;
+            for (int j0 = 0; j0 < K; j0 += 8) {
+              float4 r[8], hv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) r[u] = (j0 + u < K) ? rr[j0 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const bool nz = (r[u].x != 0.0f) | (r[u].y != 0.0f) | (r[u].z != 0.0f);
+                hv[u] = nz ? __ldg(reinterpret_cast<const float4*>(hcol + (size_t)__float_as_int(r[u].w) * 256))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                acc[0][0] = fmaf(r[u].x, hv[u].x, acc[0][0]);
+                acc[0][1] = fmaf(r[u].x, hv[u].y, acc[0][1]);
+                acc[0][2] = fmaf(r[u].x, hv[u].z, acc[0][2]);
+                acc[0][3] = fmaf(r[u].x, hv[u].w, acc[0][3]);
+                acc[1][0] = fmaf(r[u].y, hv[u].x, acc[1][0]);
+                acc[1][1] = fmaf(r[u].y, hv[u].y, acc[1][1]);
+                acc[1][2] = fmaf(r[u].y, hv[u].z, acc[1][2]);
+                acc[1][3] = fmaf(r[u].y, hv[u].w, acc[1][3]);
+                acc[2][0] = fmaf(r[u].z, hv[u].x, acc[2][0]);
+                acc[2][1] = fmaf(r[u].z, hv[u].y, acc[2][1]);
+                acc[2][2] = fmaf(r[u].z, hv[u].z, acc[2][2]);
+                acc[2][3] = fmaf(r[u].z, hv[u].w, acc[2][3]);
+              }
+            }
+          }
+          const float sc = fs[row];
+          const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
+                               (((uint32_t)q8 & 1u) << 3);
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {
+            if (n < E) {
+              uint2 hi, lo;
+              tc::split2_f16(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
+              tc::split2_f16(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
+              *reinterpret_cast<uint2*>(ab + n * 16384 + off) = hi;
+              *reinterpret_cast<uint2*>(ab + n * 16384 + 8192 + off) = lo;
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&a_full[st]);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(rec_empty);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace nmr

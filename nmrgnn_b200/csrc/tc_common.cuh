@@ -4,6 +4,7 @@
 // by the 3xTF32 products  x*w ~= hi_x*hi_w + lo_x*hi_w + hi_x*lo_w  (fp32-level accuracy,
 // accumulation in fp32 in tensor memory).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -163,6 +164,89 @@ __device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
   split_tf32(x.y, hi.y, lo.y);
   split_tf32(x.z, hi.z, lo.z);
   split_tf32(x.w, hi.w, lo.w);
+}
+
+
+// ==================================================================================
+// FP16 scaled-split products ("fp16x3"): the production tensor-core scheme.
+//   x = hi + lo * 2^-11,  hi = fp16(x),  lo = fp16((x - hi) * 2^11)      (22+ mantissa bits)
+//   x*w ~= hi_x*hi_w  +  2^-11 * (lo_x*hi_w + hi_x*lo_w)                 (dropped term ~2^-22)
+// Every fp16 x fp16 product is exact in fp32.  The main products accumulate in one TMEM
+// accumulator, the correction products in a second one; they are combined with a
+// round-to-nearest FFMA in the epilogue.  Why two accumulators: tcgen05 accumulation
+// truncates (measured on B200: -0.31 ulp per MMA instruction), so the
+// chain into the accumulator that carries the result's magnitude must be as short as
+// possible: K/16 instructions instead of the 3*K/8 of a single-accumulator 3xTF32 chain.
+// Range: operands must stay below 65504 -> activations are pre-scaled by a power of two
+// derived from an a-priori bound (exact to undo); the 2^11 scaling of `lo` keeps fp32-level
+// absolute accuracy down to 2^-35.
+// ==================================================================================
+constexpr int HK = 32;                 // fp16 K elements per 64-byte swizzled row
+constexpr int UMMA_K_F16 = 16;         // 32 bytes per instruction
+constexpr float LO_SCALE = 2048.0f;
+constexpr float LO_UNSCALE = 1.0f / 2048.0f;
+
+// Instruction descriptor: D=F32, A=B=F16, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// two floats -> packed (hi, hi) and (lo, lo) half2 words
+__device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// 8 consecutive k -> one 16-byte piece of the hi tile and one of the lo tile
+__device__ __forceinline__ void split8_f16(const float (&x)[8], uint4& hi, uint4& lo) {
+  split2_f16(x[0], x[1], hi.x, lo.x);
+  split2_f16(x[2], x[3], hi.y, lo.y);
+  split2_f16(x[4], x[5], hi.z, lo.z);
+  split2_f16(x[6], x[7], hi.w, lo.w);
+}
+
+// 32 lanes x 16 columns without the wait (issue several, then tmem_ld_wait once)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// main + corr * 2^-11 for 16 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16_combined(uint32_t t_main, uint32_t t_corr, float (&v)[16]) {
+  uint32_t a[16], b[16];
+  tmem_ld16_nowait(t_main, a);
+  tmem_ld16_nowait(t_corr, b);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(b[i]), LO_UNSCALE, __uint_as_float(a[i]));
+}
+
+// exact power of two 2^e as float (e in [-126, 127])
+__host__ __device__ __forceinline__ float pow2f_exact(int e) {
+#ifdef __CUDA_ARCH__
+  return __int_as_float((e + 127) << 23);
+#else
+  union { uint32_t u; float f; } c;
+  c.u = (uint32_t)(e + 127) << 23;
+  return c.f;
+#endif
 }
 
 }  // namespace tc

@@ -273,3 +273,12 @@ def test_tcgen05_selftest_gemm(model):
     assert e1 < 5e-3, "tcgen05 GEMM structurally wrong (layout/descriptor)"
     assert e3 < 2e-6, "3xTF32 split does not reach fp32-level accuracy"
     assert e1 > 20 * e3
+    # production scheme: fp16 scaled split, main + correction accumulators
+    h3 = model.handle.selftest_gemm(A, W, 2)
+    h1 = model.handle.selftest_gemm(A, W, 3)
+    f3 = np.abs(h3 - ref).max() / scale
+    f1 = np.abs(h1 - ref).max() / scale
+    print(f"selftest: fp16x3 err {f3:.2e}, fp16x1 err {f1:.2e}")
+    assert f1 < 5e-3, "kind::f16 GEMM structurally wrong (layout/descriptor)"
+    assert f3 < 1e-6, "fp16 scaled split does not reach fp32-level accuracy"
+    assert f1 > 20 * f3
