@@ -144,7 +144,17 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
  * accumulators (the production scheme, fp32-level accuracy), mode 3 = single FP16 product. */
 int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float* D, int mode);
 
+/* Diagnostic: the round-toward-zero compensation constants of the tensor-core path, in units of
+ * 2^-24 (c such that the epilogue multiplies the accumulator by 1 + c * 2^-24): c_ulp[0] = edge-MLP
+ * layers (analytic), c_ulp[1 + l] = MP layer l (calibrated against the FFMA kernels when the model is
+ * created).  Returns the number of values written (n_mp + 1; 1 if the MP layers are not on tensor
+ * cores) or a negative status. */
+int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap);
+
 /* Runtime options (value semantics per name):
+ *   "tc_compensate" = 0: switch the compensation above off (diagnostics only; default 1);
+ *   "tc_min_atoms" = n: calls with fewer than n atoms run on the exact-FP32 kernels (default 4096: below
+ *                     one tile per SM both paths take one wave; 0 = always use tensor cores);
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "profile"    = 1: nmrgnn_forward records CUDA events (on the launching stream) around its
  *                     stages; read them with nmrgnn_stage_times. */

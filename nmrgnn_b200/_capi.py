@@ -21,7 +21,7 @@ EXPORTS = [
     "nmrgnn_abi_version", "nmrgnn_num_weights", "nmrgnn_create", "nmrgnn_destroy", "nmrgnn_forward",
     "nmrgnn_edge_features", "nmrgnn_embed", "nmrgnn_mp_layer", "nmrgnn_fc_readout", "nmrgnn_synchronize",
     "nmrgnn_kernel_launches", "nmrgnn_compute_path", "nmrgnn_last_error", "nmrgnn_knn_graph",
-    "nmrgnn_set_option", "nmrgnn_selftest_gemm", "nmrgnn_stage_times",
+    "nmrgnn_set_option", "nmrgnn_selftest_gemm", "nmrgnn_stage_times", "nmrgnn_tc_compensation",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library() -> C.CDLL:
     lib.nmrgnn_set_option.argtypes = [vp, C.c_char_p, C.c_int]
     lib.nmrgnn_selftest_gemm.argtypes = [vp, fp, fp, fp, C.c_int]
     lib.nmrgnn_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.nmrgnn_tc_compensation.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     if lib.nmrgnn_abi_version() != 1:
         raise ImportError("libnmrgnn_b200.so ABI version mismatch")
     _lib = lib
@@ -143,6 +144,14 @@ class Handle:
             self.check(n)
         ms = [float(buf[i]) for i in range(n)]
         return {"edge": ms[0], "embed": ms[1], "mp_layers": ms[2:n - 1], "fc_readout": ms[n - 1]}
+
+    def tc_compensation(self) -> dict:
+        """Round-toward-zero compensation constants of the tensor-core path, in units of 2^-24."""
+        buf = (C.c_float * 80)()
+        n = self._lib.nmrgnn_tc_compensation(self._h, buf, 80)
+        if n < 0:
+            self.check(n)
+        return {"edge": float(buf[0]), "mp_layers": [float(buf[i]) for i in range(1, n)]}
 
     def synchronize(self, stream: Optional[int] = None) -> None:
         self.check(self._lib.nmrgnn_synchronize(self._h, stream))

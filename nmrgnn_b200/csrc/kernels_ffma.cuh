@@ -182,6 +182,7 @@ struct MpArgs {
   int64_t n_atoms;
   int K;
   int act;
+  int raw;                 // 1: h_out = inv_degree * D (no activation, no residual) -- calibration tap
 };
 
 constexpr int MP_F = 256;
@@ -276,14 +277,19 @@ __global__ void __launch_bounds__(MP_THREADS, 1) mp_layer_ffma_kernel(const MpAr
         const float4 hA = *reinterpret_cast<const float4*>(p.h_in + atom * MP_F + c0);
         const float4 hB = *reinterpret_cast<const float4*>(p.h_in + atom * MP_F + c0 + 64);
         float4 oA, oB;
-        oA.x = apply_act(acc[i][0] * s, p.act) + hA.x;
-        oA.y = apply_act(acc[i][1] * s, p.act) + hA.y;
-        oA.z = apply_act(acc[i][2] * s, p.act) + hA.z;
-        oA.w = apply_act(acc[i][3] * s, p.act) + hA.w;
-        oB.x = apply_act(acc[i][4] * s, p.act) + hB.x;
-        oB.y = apply_act(acc[i][5] * s, p.act) + hB.y;
-        oB.z = apply_act(acc[i][6] * s, p.act) + hB.z;
-        oB.w = apply_act(acc[i][7] * s, p.act) + hB.w;
+        if (p.raw) {
+          oA = make_float4(acc[i][0] * s, acc[i][1] * s, acc[i][2] * s, acc[i][3] * s);
+          oB = make_float4(acc[i][4] * s, acc[i][5] * s, acc[i][6] * s, acc[i][7] * s);
+        } else {
+          oA.x = apply_act(acc[i][0] * s, p.act) + hA.x;
+          oA.y = apply_act(acc[i][1] * s, p.act) + hA.y;
+          oA.z = apply_act(acc[i][2] * s, p.act) + hA.z;
+          oA.w = apply_act(acc[i][3] * s, p.act) + hA.w;
+          oB.x = apply_act(acc[i][4] * s, p.act) + hB.x;
+          oB.y = apply_act(acc[i][5] * s, p.act) + hB.y;
+          oB.z = apply_act(acc[i][6] * s, p.act) + hB.z;
+          oB.w = apply_act(acc[i][7] * s, p.act) + hB.w;
+        }
         *reinterpret_cast<float4*>(p.h_out + atom * MP_F + c0) = oA;
         *reinterpret_cast<float4*>(p.h_out + atom * MP_F + c0 + 64) = oB;
       }

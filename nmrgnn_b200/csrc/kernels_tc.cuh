@@ -503,6 +503,10 @@ __global__ void __launch_bounds__(256) row_absmax256_kernel(const float* __restr
 // 32 k), scale each row by a power of two from an a-priori bound (fp16 range), split it into
 // the hi/lo operand tiles and hand it to the MMA warp through a 2-pass ring; W' streams
 // through a 3-slot ring of 32 KB bulk copies.  T never reaches HBM.
+// The gather is the critical resource: every producer thread keeps 8-16 independent 16-byte
+// row loads in flight (two register buffers of 8, the next half-step is issued before the
+// current one is consumed, across step and pass boundaries), loads are unconditional (padded
+// slots read row 0 with a zero edge feature) and edge records come from shared memory.
 //   warp 0: W' loader   warp 1: MMA issuer + TMEM owner   warp 2: edge-record loader
 //   warps 4-7: epilogue (thread = atom row)                warps 8-15: producers
 // ----------------------------------------------------------------------------------
@@ -518,6 +522,8 @@ struct MpTcArgs {
   int K;
   int E;
   int act;
+  float corr;                // 1 + c: compensates the round-toward-zero accumulation of tcgen05
+  int raw;                   // 1: h_out = inv_degree * D (no activation, no residual) -- calibration tap
 };
 
 constexpr int MTC_THREADS = 512;
@@ -535,7 +541,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
   uint8_t* b_ring = a_st + 2 * 3 * 16384;                 // [BRING][hi 16384 | lo 16384]
   float4* rec_s = reinterpret_cast<float4*>(b_ring + MTC_BRING * 32768);   // [128 * K]
   float* fscale = reinterpret_cast<float*>(rec_s + 128 * MTC_KMAX);        // [2][128]  2^-s
-  float* oscale = fscale + 2 * 128;                                         // [2][128]  2^s * inv_degree
+  float* oscale = fscale + 2 * 128;                                         // [2][128]  2^s * inv_degree * corr
   uint64_t* bars = reinterpret_cast<uint64_t*>(oscale + 2 * 128);
   uint64_t* a_full = bars;            // [2]
   uint64_t* a_empty = a_full + 2;     // [2]
@@ -646,27 +652,44 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       const int64_t a0 = tile * 128;
       const int rows = (int)min((int64_t)128, p.n_atoms - a0);
       const bool valid = row < rows;
-      const int64_t atom = a0 + row;
+      const int64_t atom = valid ? a0 + row : a0;        // invalid rows read a valid address, write nothing
+      const float* hin = p.h_in + atom * 256;
+      float* hout = p.h_out + atom * 256;
+      // the residual row is prefetched one 16-column group ahead of the accumulator reads
+      float4 res[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) res[j] = tc::ldg128(hin + j * 4);
       tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
       const float osc = oscale[(t & 1) * 128 + row];
       tc::mbar_wait(d_full, t & 1);
       tc::tc_fence_after();
-      const float* hin = p.h_in + atom * 256;
-      float* hout = p.h_out + atom * 256;
       float hm = 0.0f;
 #pragma unroll 1
       for (int cc = 0; cc < 16; ++cc) {
         float v[16];
         tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
+        float4 cur[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = res[j];
+        if (cc + 1 < 16) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[j] = tc::ldg128(hin + (cc + 1) * 16 + j * 4);
+        }
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 r = *reinterpret_cast<const float4*>(hin + cc * 16 + j * 4);
             float4 o;
-            o.x = apply_act(v[j * 4 + 0] * osc, p.act) + r.x;
-            o.y = apply_act(v[j * 4 + 1] * osc, p.act) + r.y;
-            o.z = apply_act(v[j * 4 + 2] * osc, p.act) + r.z;
-            o.w = apply_act(v[j * 4 + 3] * osc, p.act) + r.w;
+            if (p.raw) {
+              o.x = v[j * 4 + 0] * osc;
+              o.y = v[j * 4 + 1] * osc;
+              o.z = v[j * 4 + 2] * osc;
+              o.w = v[j * 4 + 3] * osc;
+            } else {
+              o.x = apply_act(v[j * 4 + 0] * osc, p.act) + cur[j].x;
+              o.y = apply_act(v[j * 4 + 1] * osc, p.act) + cur[j].y;
+              o.z = apply_act(v[j * 4 + 2] * osc, p.act) + cur[j].z;
+              o.w = apply_act(v[j * 4 + 3] * osc, p.act) + cur[j].w;
+            }
             hm = fmaxf(hm, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
             *reinterpret_cast<float4*>(hout + cc * 16 + j * 4) = o;
           }
@@ -683,6 +706,9 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
     const int ptid = tid - 256;              // 0..255
     const int q8 = lane & 7;                 // 4-feature group inside the 32-feature pass
     const int rsub = lane >> 3;              // row inside the warp's 4-row group
+    const uint32_t rec_a = tc::smem_u32(rec_s);
+    const uint32_t ast_a = tc::smem_u32(a_st);
+    const float* hq = p.h_in + q8 * 4;
     uint32_t pass = 0, t = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int64_t a0 = tile * 128;
@@ -690,13 +716,55 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       float* fs = fscale + (t & 1) * 128;
       float* os = oscale + (t & 1) * 128;
       tc::mbar_wait(rec_full, t & 1);
+
+      // 8 independent row loads of half-step (row, half) at feature pass ps
+      // (no branches around the loads: a branch makes the compiler drain every outstanding load first;
+      //  out-of-range rows / slots read an in-bounds shared address and are neutralised by selects)
+      auto issue = [&](float4 (&hv)[8], int row, int half, int ps) {
+        const bool rv = row < rows;
+        const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u + 12u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          uint32_t idx = tc::lds32(ra + u * 16);
+          idx = (rv && half * 8 + u < K) ? idx : 0u;
+          hv[u] = tc::ldg128(hq + (size_t)idx * 256 + ps * 32);
+        }
+      };
+      auto consume = [&](const float4 (&hv)[8], int row, int half, float (&acc)[3][4]) {
+        const bool rv = row < rows;
+        const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 r = tc::lds128(ra + u * 16);
+          const bool ok = rv && half * 8 + u < K;
+          r.x = ok ? r.x : 0.0f;
+          r.y = ok ? r.y : 0.0f;
+          r.z = ok ? r.z : 0.0f;
+          acc[0][0] = fmaf(r.x, hv[u].x, acc[0][0]);
+          acc[0][1] = fmaf(r.x, hv[u].y, acc[0][1]);
+          acc[0][2] = fmaf(r.x, hv[u].z, acc[0][2]);
+          acc[0][3] = fmaf(r.x, hv[u].w, acc[0][3]);
+          acc[1][0] = fmaf(r.y, hv[u].x, acc[1][0]);
+          acc[1][1] = fmaf(r.y, hv[u].y, acc[1][1]);
+          acc[1][2] = fmaf(r.y, hv[u].z, acc[1][2]);
+          acc[1][3] = fmaf(r.y, hv[u].w, acc[1][3]);
+          acc[2][0] = fmaf(r.z, hv[u].x, acc[2][0]);
+          acc[2][1] = fmaf(r.z, hv[u].y, acc[2][1]);
+          acc[2][2] = fmaf(r.z, hv[u].z, acc[2][2]);
+          acc[2][3] = fmaf(r.z, hv[u].w, acc[2][3]);
+        }
+      };
+
+      float4 hvA[8], hvB[8];
+      issue(hvA, pw * 4 + rsub, 0, 0);       // first half-step of the tile, in flight during the scale pass
+
       // per-row bound |T[i,.]| <= sum_j max_n|e_ijn| * hmax[nl_ij]  ->  power-of-two scale
       {
         const int row = ptid >> 1, hf = ptid & 1;
         float b = 0.0f;
         if (row < rows) {
           for (int j = hf; j < K; j += 2) {
-            const float4 r = rec_s[row * K + j];
+            const float4 r = tc::lds128(rec_a + (uint32_t)(row * K + j) * 16u);
             const float em = fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fabsf(r.z));
             if (em != 0.0f) b = fmaf(em, __ldg(p.hmax_in + __float_as_int(r.w)), b);
           }
@@ -708,16 +776,16 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           s = b > 0.0f ? max(s, 0) : 0;
           s = min(s, 100);
           fs[row] = tc::pow2f_exact(-s);
-          os[row] = row < rows ? tc::pow2f_exact(s) * p.inv_degree[a0 + row] : 0.0f;
+          os[row] = row < rows ? tc::pow2f_exact(s) * p.inv_degree[a0 + row] * p.corr : 0.0f;
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (lane == 0) tc::mbar_arrive(&sc_full[t & 1]);
+
       for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
         const uint32_t st = pass & 1;
         tc::mbar_wait(&a_empty[st], ((pass >> 1) & 1) ^ 1);
-        uint8_t* ab = a_st + st * 3 * 16384;
-        const float* hcol = p.h_in + ps * 32 + q8 * 4;
+        const uint32_t ab = ast_a + st * 3 * 16384;
 #pragma unroll 1
         for (int step = 0; step < 4; ++step) {
           const int row = step * 32 + pw * 4 + rsub;
@@ -726,35 +794,16 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           for (int n = 0; n < 3; ++n)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
-          if (row < rows) {
-            const float4* rr = rec_s + row * K;
-            for (int j0 = 0; j0 < K; j0 += 8) {
-              float4 r[8], hv[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) r[u] = (j0 + u < K) ? rr[j0 + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                const bool nz = (r[u].x != 0.0f) | (r[u].y != 0.0f) | (r[u].z != 0.0f);
-                hv[u] = nz ? __ldg(reinterpret_cast<const float4*>(hcol + (size_t)__float_as_int(r[u].w) * 256))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                acc[0][0] = fmaf(r[u].x, hv[u].x, acc[0][0]);
-                acc[0][1] = fmaf(r[u].x, hv[u].y, acc[0][1]);
-                acc[0][2] = fmaf(r[u].x, hv[u].z, acc[0][2]);
-                acc[0][3] = fmaf(r[u].x, hv[u].w, acc[0][3]);
-                acc[1][0] = fmaf(r[u].y, hv[u].x, acc[1][0]);
-                acc[1][1] = fmaf(r[u].y, hv[u].y, acc[1][1]);
-                acc[1][2] = fmaf(r[u].y, hv[u].z, acc[1][2]);
-                acc[1][3] = fmaf(r[u].y, hv[u].w, acc[1][3]);
-                acc[2][0] = fmaf(r[u].z, hv[u].x, acc[2][0]);
-                acc[2][1] = fmaf(r[u].z, hv[u].y, acc[2][1]);
-                acc[2][2] = fmaf(r[u].z, hv[u].z, acc[2][2]);
-                acc[2][3] = fmaf(r[u].z, hv[u].w, acc[2][3]);
-              }
-            }
+          issue(hvB, row, 1, ps);
+          consume(hvA, row, 0, acc);
+          {
+            // next half-step: next row group of this pass, or the first one of the next pass
+            const bool last = step == 3;
+            const int nrow = last ? pw * 4 + rsub : row + 32;
+            const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);   // (the tile's very last prefetch is unused)
+            issue(hvA, nrow, 0, nps);
           }
+          consume(hvB, row, 1, acc);
           const float sc = fs[row];
           const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
                                (((uint32_t)q8 & 1u) << 3);
@@ -764,8 +813,8 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
               uint2 hi, lo;
               tc::split2_f16(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
               tc::split2_f16(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
-              *reinterpret_cast<uint2*>(ab + n * 16384 + off) = hi;
-              *reinterpret_cast<uint2*>(ab + n * 16384 + 8192 + off) = lo;
+              tc::sts64(ab + n * 16384 + off, hi.x, hi.y);
+              tc::sts64(ab + n * 16384 + 8192 + off, lo.x, lo.y);
             }
           }
         }
@@ -775,6 +824,302 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(rec_empty);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace nmr
+
+namespace nmr {
+
+// ----------------------------------------------------------------------------------
+// Node MLP + readout on tensor cores, F = 256 (FCBlock + out_layer + peak standardisation;
+// model.py:191-196, 268-273).  One CTA = 128 atoms per tile, persistent over tiles.
+// The node tile X lives in shared memory as the fp16x3 A operand (hi | lo, 8 K-chunks of
+// 32 features); every residual layer X <- act(X W + b) + X is
+//   MMA:      D[128 x 256] = X * W     two N = 128 halves per K-chunk, main / corr accumulators in TMEM
+//   epilogue: thread = (atom row, 128-column half): D -> RZ compensation -> bias -> act -> + x_old
+//             (x_old is re-assembled from the hi/lo pair it is about to overwrite: 22 mantissa bits,
+//              round-to-nearest) -> split -> written back in place as the next layer's operand.
+// The last layer (256 -> 128, no residual) leaves Z in fp32 in shared memory (overlaying X, whose
+// MMAs have completed) for the warp-per-atom readout.  W streams through a ring of 16 KB bulk
+// copies (one K-chunk x one N-half).  Rows are pre-scaled by a power of two from an a-priori
+// affine bound of |x| per layer (fp16 range); the scale is exact to undo.
+//   warp 0: W loader   warp 1: MMA issuer + TMEM owner   warps 2-9: load / epilogue / readout
+// ----------------------------------------------------------------------------------
+struct FcTcArgs {
+  const float* nodes;        // [n_atoms, 256]
+  const float* atoms;        // [n_atoms, C]
+  float* peaks;              // [n_atoms]
+  float* fc_nodes;           // optional [n_atoms, 128]
+  int64_t n_atoms;
+  int C;
+  const uint8_t* Wimg;       // layers 0..n-2: [8 chunks][2 halves][hi 8192 | lo 8192]; last: [8 chunks][hi | lo]
+  const float* bias;         // [n_layers][256]
+  float gain[MAX_DENSE];     // |x_l| <= gain[l] * max|x_0| + offs[l]   (input of layer l)
+  float offs[MAX_DENSE];
+  int n_layers;
+  int act;
+  float corr;                // 1 + c: round-toward-zero compensation for a 16-instruction chain
+  const float* Wo;           // [128, C]
+  const float* bo;           // [C]
+  const float* peak_std;     // [C]
+  const float* peak_avg;     // [C]
+};
+
+constexpr int FTC_THREADS = 320;
+constexpr int FTC_RING = 5;
+constexpr int FTC_LDZ = 132;
+constexpr size_t FTC_X_BYTES = 8 * 16384;
+constexpr size_t FTC_SMEM = 1024 + FTC_X_BYTES + FTC_RING * 16384 + MAX_DENSE * 256 * 4 + MAX_DENSE * 128 * 4 + 256;
+static_assert(FTC_SMEM <= 227 * 1024, "node-MLP tensor-core kernel exceeds the 227 KB shared-memory limit");
+static_assert(128 * FTC_LDZ * 4 <= FTC_X_BYTES, "Z overlays the X operand");
+
+__global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcTcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xs = smem;                                      // [8 chunks][hi 8192 | lo 8192]; later Z [128][FTC_LDZ] fp32
+  uint8_t* ring = xs + FTC_X_BYTES;                        // [RING][hi 8192 | lo 8192]
+  float* bias_s = reinterpret_cast<float*>(ring + FTC_RING * 16384);   // [n_layers][256]
+  float* rs = bias_s + MAX_DENSE * 256;                    // [n_layers][128] per-row 2^-s of the layer's input
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rs + MAX_DENSE * 128);
+  uint64_t* w_full = bars;                                 // [RING]
+  uint64_t* w_empty = w_full + FTC_RING;                   // [RING]
+  uint64_t* x_full = w_empty + FTC_RING;
+  uint64_t* d_full = x_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < FTC_RING; ++i) {
+      tc::mbar_init(&w_full[i], 1);
+      tc::mbar_init(&w_empty[i], 1);
+    }
+    tc::mbar_init(x_full, 8);
+    tc::mbar_init(d_full, 1);
+    tc::mbar_fence_init();
+  }
+  const int nl = p.n_layers;
+  for (int i = tid; i < nl * 256; i += FTC_THREADS) bias_s[i] = p.bias[i];
+  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t n_tiles = (p.n_atoms + 127) / 128;
+
+  if (warp == 0) {
+    // ===================== W loader =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int l = 0; l < nl; ++l) {
+          const int n_slots = (l == nl - 1) ? 8 : 16;
+          const uint8_t* src = p.Wimg + (size_t)l * 16 * 16384;
+          for (int q = 0; q < n_slots; ++q, ++it) {
+            const uint32_t slot = it % FTC_RING, ph = (it / FTC_RING) & 1;
+            tc::mbar_wait(&w_empty[slot], ph ^ 1);
+            tc::mbar_expect_tx(&w_full[slot], 16384);
+            tc::bulk_g2s(ring + slot * 16384, src + (size_t)q * 16384, 16384, &w_full[slot]);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(128, 128);
+      uint32_t it = 0, px = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int l = 0; l < nl; ++l) {
+          const int halves = (l == nl - 1) ? 1 : 2;
+          tc::mbar_wait(x_full, px);
+          px ^= 1;
+          tc::tc_fence_after();
+          for (int c = 0; c < 8; ++c) {
+            const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(xs + c * 16384));
+            const uint64_t al = tc::make_desc_sw64(tc::smem_u32(xs + c * 16384 + 8192));
+            for (int hf = 0; hf < halves; ++hf, ++it) {
+              const uint32_t slot = it % FTC_RING;
+              tc::mbar_wait(&w_full[slot], (it / FTC_RING) & 1);
+              tc::tc_fence_after();
+              const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
+              const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
+              const uint32_t d_main = tmem_base + (uint32_t)hf * 128u, d_corr = d_main + 256u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                tc::umma_f16(d_main, ah + adv, bh + adv, idesc, (c | ks) != 0);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, (c | ks) != 0);
+                tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+              }
+              tc::umma_commit(&w_empty[slot]);
+            }
+          }
+          tc::umma_commit(d_full);
+        }
+    }
+  } else {
+    // ===================== load / epilogue / readout warps =====================
+    const int we = warp - 2;                 // 0..7
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    // warps 2..9: warp%4 = {2,3,0,1,2,3,0,1}; the first four (we 0..3) take columns 0..127, the others 128..255
+    const int half = we >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t xs_a = tc::smem_u32(xs);
+    const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t_corr = t_main + 256u;
+    float* Z = reinterpret_cast<float*>(xs);
+    uint32_t pd = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int64_t a0 = tile * 128;
+      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      // ---- stage the node tile: warp `we` loads rows we, we+8, ... (1 KB coalesced per row),
+      //      lane = 8 consecutive features = one 16-byte piece of the hi tile and one of the lo tile
+      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's readout has finished with Z
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int r = we + i * 8;
+        float x[8];
+        if (r < rows) {
+          const float* src = p.nodes + (a0 + r) * 256 + lane * 8;
+          const float4 x0 = tc::ldg128(src), x1 = tc::ldg128(src + 4);
+          x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
+          x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) x[u] = 0.0f;
+        }
+        float m = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m = fmaxf(m, fabsf(x[u]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        // per-layer power-of-two input scale from the affine bound of |x_l|
+        float s0 = 1.0f;
+        if (lane < nl) {
+          const float b = fmaf(p.gain[lane], m, p.offs[lane]);
+          int s = ((__float_as_int(b) >> 23) & 0xff) - 127 - 14;
+          s = (b > 0.0f && b < 3.0e38f) ? min(max(s, 0), 100) : 0;
+          rs[lane * 128 + r] = tc::pow2f_exact(-s);
+          if (lane == 0) s0 = tc::pow2f_exact(-s);
+        }
+        s0 = __shfl_sync(0xffffffffu, s0, 0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] *= s0;
+        uint4 hi, lo;
+        tc::split8_f16(x, hi, lo);
+        const uint32_t off = xs_a + (uint32_t)(lane >> 2) * 16384u + tc::sw64_chunk_offset(r, lane & 3);
+        tc::sts128(off, hi);
+        tc::sts128(off + 8192u, lo);
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(x_full);
+
+      // ---- residual layers
+      for (int l = 0; l + 1 < nl; ++l) {
+        tc::mbar_wait(d_full, pd);
+        pd ^= 1;
+        tc::tc_fence_after();
+        const float* bl = bias_s + l * 256 + half * 128;
+        const float s_in = rs[l * 128 + row];              // 2^-s of this layer's input
+        const float s_nx = rs[(l + 1) * 128 + row];        // 2^-s' of the next layer's input
+        const float s_old = __fdiv_rn(1.0f, s_in);         // exact: s_in is a power of two
+        const float s_out = p.corr * s_old;                // accumulator -> true scale, with the RZ compensation
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+          float v[16];
+          const int col = half * 128 + cc * 16;
+          tc::tmem_ld16_combined(t_main + col, t_corr + col, v);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int k0 = col + hh * 8;
+            const uint32_t off = xs_a + (uint32_t)(k0 >> 5) * 16384u + tc::sw64_chunk_offset(row, (k0 & 31) >> 3);
+            uint4 ohi, olo;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ohi.x), "=r"(ohi.y), "=r"(ohi.z), "=r"(ohi.w) : "r"(off));
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(olo.x), "=r"(olo.y), "=r"(olo.z), "=r"(olo.w) : "r"(off + 8192u));
+            const uint32_t oh[4] = {ohi.x, ohi.y, ohi.z, ohi.w}, ol[4] = {olo.x, olo.y, olo.z, olo.w};
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&oh[i]));
+              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ol[i]));
+              const float old0 = fmaf(fl.x, tc::LO_UNSCALE, fh.x) * s_old;
+              const float old1 = fmaf(fl.y, tc::LO_UNSCALE, fh.y) * s_old;
+              x[2 * i] = (apply_act(fmaf(v[hh * 8 + 2 * i], s_out, bl[cc * 16 + hh * 8 + 2 * i]), p.act) + old0) * s_nx;
+              x[2 * i + 1] = (apply_act(fmaf(v[hh * 8 + 2 * i + 1], s_out, bl[cc * 16 + hh * 8 + 2 * i + 1]), p.act) + old1) * s_nx;
+            }
+            uint4 hi, lo;
+            tc::split8_f16(x, hi, lo);
+            tc::sts128(off, hi);
+            tc::sts128(off + 8192u, lo);
+          }
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(x_full);
+      }
+      // ---- last layer: Z = act(D + b), 128 columns; each (row, half) thread takes 64 of them
+      {
+        const int l = nl - 1;
+        tc::mbar_wait(d_full, pd);
+        pd ^= 1;
+        tc::tc_fence_after();
+        const float s_out = p.corr * __fdiv_rn(1.0f, rs[l * 128 + row]);
+        const float* bl = bias_s + l * 256 + half * 64;
+        float* zr = Z + row * FTC_LDZ + half * 64;
+        // all MMAs that read X have completed (d_full); every warp must be past its own X reads too
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[16];
+          const int col = half * 64 + cc * 16;
+          tc::tmem_ld16_combined(t_main + col, t_corr + col, v);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 o;
+            o.x = apply_act(fmaf(v[i + 0], s_out, bl[cc * 16 + i + 0]), p.act);
+            o.y = apply_act(fmaf(v[i + 1], s_out, bl[cc * 16 + i + 1]), p.act);
+            o.z = apply_act(fmaf(v[i + 2], s_out, bl[cc * 16 + i + 2]), p.act);
+            o.w = apply_act(fmaf(v[i + 3], s_out, bl[cc * 16 + i + 3]), p.act);
+            *reinterpret_cast<float4*>(zr + cc * 16 + i) = o;
+          }
+        }
+        tc::tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      if (p.fc_nodes != nullptr) {
+        for (int i = tid - 64; i < rows * 128; i += 256) {
+          const int r = i >> 7, k = i & 127;
+          p.fc_nodes[(a0 + r) * 128 + k] = Z[r * FTC_LDZ + k];
+        }
+      }
+      // ---- readout: peaks = sum_c (z . Wo[:,c] + bo[c]) * a[c] * std[c] + a[c] * avg[c]; warp per atom,
+      //      skipping classes with a[c] == 0 (exact for finite activations)
+      for (int i = 0; i < 16; ++i) {
+        const int r = we * 16 + i;
+        if (r >= rows) break;
+        const int64_t atom = a0 + r;
+        const float* zr = Z + r * FTC_LDZ;
+        float peak = 0.0f;
+        for (int c = 0; c < p.C; ++c) {
+          const float a = p.atoms[atom * p.C + c];
+          if (a != 0.0f) {
+            float dot = 0.0f;
+#pragma unroll
+            for (int k = lane; k < 128; k += 32) dot = fmaf(zr[k], __ldg(p.Wo + k * p.C + c), dot);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            const float full = dot + p.bo[c];
+            peak += full * a * p.peak_std[c] + a * p.peak_avg[c];
+          }
+        }
+        if (lane == 0) p.peaks[atom] = peak;
+      }
     }
   }
   tc::tc_fence_before();

@@ -40,6 +40,7 @@ def main():
     plin = dataclasses.replace(p, mp_activation="linear", fc_activation="linear")
     m = nmrgnn_b200.GNNModel(plin)
     print("path:", m.handle.compute_path)
+    print("tc compensation (x 2^-24):", m.handle.tc_compensation())
     rng = np.random.default_rng(0)
     A = rng.uniform(0.5, 1.5, size=(128, 64)).astype(np.float16).astype(np.float32)
     W = rng.uniform(0.5, 1.5, size=(64, 128)).astype(np.float16).astype(np.float32)
@@ -70,6 +71,26 @@ def main():
             x = x * (g["edges"] > 0)[..., None]
             stats(f"{gname} {path:4s} edge(linear chain)", e3, x)
     m.handle.set_option("force_ffma", 0)
+    # natural (uncompensated) slopes per layer on the synthetic workloads, real-model activations as inputs
+    from nmrgnn_b200 import workloads
+    from oracle import forward as orc
+    m.handle.set_option("tc_compensate", 0)
+    m.handle.set_option("tc_min_atoms", 0)
+    for wname, b in (("protein_batch", workloads.protein_batch(2, first_seed=7)),
+                     ("small_molecules", workloads.small_molecule_batch(96, first_seed=3))):
+        atoms, nlist, edges, inv, offs = b
+        inter = {}
+        orc.forward(p, atoms, nlist, edges, inv, dtype=np.float64, intermediates=inter)
+        e3 = inter["edge_features"].astype(np.float32)
+        hs = [inter["embed"].astype(np.float32)] + [h.astype(np.float32) for h in inter["mp_nodes"][:-1]]
+        ok = inv > 0
+        for l in range(4):
+            out = m.mp_block.mp[l]([hs[l], nlist, e3, inv])
+            d_gpu = (out.astype(np.float64) - hs[l].astype(np.float64))[ok] / inv.astype(np.float64)[ok, None]
+            T = np.einsum("ijn,ijl->iln", e3.astype(np.float64), hs[l][nlist].astype(np.float64))
+            d_ref = np.einsum("iln,lmn->im", T, p.mp_w[l].astype(np.float64))[ok]
+            stats(f"{wname} (uncompensated) mp{l}", d_gpu, d_ref)
+    m.handle.set_option("tc_compensate", 1)
 
 
 if __name__ == "__main__":

@@ -21,6 +21,7 @@ def tf32(x):
 def main():
     m = nmrgnn_b200.load_model()
     print("path:", m.handle.compute_path)
+    print("tc compensation (x 2^-24):", m.handle.tc_compensation())
     rng = np.random.default_rng(0)
     # 1. accumulation: tf32-exact positive inputs -> every product exact, only the adds round
     A = rng.uniform(0.5, 1.5, size=(128, 64)).astype(np.float16).astype(np.float32)   # exact in fp16 and tf32
