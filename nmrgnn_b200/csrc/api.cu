@@ -310,6 +310,7 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     }
     t.centers = h->centers;
     t.gap = h->gap;
+    t.rbf_c = (float)(-1.4426950408889634 / (double)h->gap);
     t.Wimg = h->edge_img;
     t.Wfimg = h->edge_f_img;
     t.bias = h->edge_bias;

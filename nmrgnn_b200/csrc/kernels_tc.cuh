@@ -199,9 +199,9 @@ __global__ void __launch_bounds__(192, 1) tc_selftest_f16_kernel(const float* __
 // main/corr accumulators (2 x 128 columns) in tensor memory.
 //   warp 0       : weight loader (one lane): 16 KB bulk copies into a 4-slot ring
 //   warp 1       : MMA issuer (one lane) + TMEM owner
-//   warps 2..9   : epilogue group of slot 0;  warps 10..17: slot 1.  Within a group,
-//                  warp%4 selects the TMEM lane quarter (32 edges) and the warp's rank in
-//                  its quarter selects a 64-column half: thread = (edge row, 64 features).
+//   warps 2..17  : epilogue; all 16 warps work on slot 0, then slot 1, then slot 0 ... :
+//                  warp%4 selects the TMEM lane quarter (32 edges), (warp-2)/4 the 32-column
+//                  K-chunk: thread = (edge row, 32 features).
 // The last (linear, 128 -> E) layer is one more MMA with N = 16 (E padded) against the
 // resident final-layer weights.
 // ----------------------------------------------------------------------------------
@@ -212,6 +212,7 @@ struct EdgeTcArgs {
   int64_t n_edges;
   const float* centers;      // [128]
   float gap;
+  float rbf_c;               // -log2(e) / gap
   const uint8_t* Wimg;       // hidden layers: [n_hidden][4 chunks][hi 8192 | lo 8192]
   const uint8_t* Wfimg;      // final layer:   [4 chunks][hi 1024 | lo 1024]   (16 rows, rows >= E are zero)
   const float* bias;         // [n_hidden][128]
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
       tc::mbar_init(&w_empty[i], 1);
     }
     for (int g = 0; g < 2; ++g) {
-      tc::mbar_init(&x_full[g], 8);
+      tc::mbar_init(&x_full[g], 16);
       tc::mbar_init(&d_full[g], 1);
     }
     tc::mbar_init(wf_full, 1);
@@ -344,53 +345,59 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
           }
     }
   } else {
-    // ===================== epilogue groups: thread = (edge row, 64 features) =====================
-    const int we = warp - 2;
-    const int g = we >> 3;
-    const int q = warp & 3;
-    const int half = (we & 7) >> 2;
+    // ===================== epilogue warps: thread = (edge row, 32 features = one K-chunk) =====================
+    // All 16 warps work on one slot at a time (slot 0, slot 1, slot 0, ...), so that the MMAs of one slot
+    // always overlap the CUDA-core work of the other and no warp group waits for its own slot's MMAs.
+    const int we = warp - 2;                 // 0..15
+    const int q = warp & 3;                  // TMEM lane quarter
+    const int cq = we >> 2;                  // column quarter = K-chunk written by this thread
     const int row = q * 32 + lane;
-    const int col0 = half * 64;
-    uint8_t* xg = xs + g * ETC_X_BYTES;
-    const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
-    const uint32_t t_corr = t_main + 128u;
-    uint32_t pd = 0;
-    for (int n = g; n < n_my; n += 2) {
-      const int64_t tile = blockIdx.x + (int64_t)n * gridDim.x;
-      const int64_t e = tile * 128 + row;
-      float d = 0.0f;
-      int32_t idx = 0;
-      if (e < p.n_edges) {
-        d = p.edges[e];
-        if (p.nlist != nullptr && half == 0) {
-          idx = p.nlist[e];
-          if (idx < 0 || idx >= p.n_atoms) {
-            atomicOr(p.err_flag, 1);
-            idx = 0;
+    const int col0 = cq * 32;
+    const uint32_t xs_a = tc::smem_u32(xs);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t pd[2] = {0, 0};
+    for (int pair = 0; pair * 2 < n_my; ++pair) {
+      const int n_in_pair = min(2, n_my - pair * 2);
+      float dd[2];
+      int32_t idxs[2] = {0, 0};
+      int64_t eidx[2];
+      // pass 0: RBF expansion * mask  (layers.py:137-140, model.py:251-257)
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g >= n_in_pair) continue;
+        const int64_t tile = blockIdx.x + (int64_t)(pair * 2 + g) * gridDim.x;
+        const int64_t e = tile * 128 + row;
+        eidx[g] = e;
+        float d = 0.0f;
+        if (e < p.n_edges) {
+          d = __ldg(p.edges + e);
+          if (p.nlist != nullptr && cq == 0) {
+            int32_t idx = __ldg(p.nlist + e);
+            if (idx < 0 || idx >= p.n_atoms) {
+              atomicOr(p.err_flag, 1);
+              idx = 0;
+            }
+            idxs[g] = idx;
           }
         }
-      }
-      const bool m = d > 0.0f;
-      // pass 0: RBF expansion * mask  (layers.py:137-140, model.py:251-257)
-      {
-        const float s_in = p.in_scale[0];
+        dd[g] = d;
+        const bool m = d > 0.0f;
+        const float s_in = m ? p.in_scale[0] : 0.0f;
+        const uint32_t xg = xs_a + (uint32_t)g * ETC_X_BYTES + (uint32_t)cq * 16384u;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int j = 0; j < 4; ++j) {
+          float x[8];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float x[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float diff = d - cen_s[col0 + cc * 16 + hh * 8 + i];
-              const float v = expf(__fdiv_rn(-__fmul_rn(diff, diff), p.gap));
-              x[i] = m ? v * s_in : 0.0f;
-            }
-            uint4 hi, lo;
-            tc::split8_f16(x, hi, lo);
-            const uint32_t off = (uint32_t)(half * 2 + (cc >> 1)) * 16384u + tc::sw64_chunk_offset(row, (cc & 1) * 2 + hh);
-            *reinterpret_cast<uint4*>(xg + off) = hi;
-            *reinterpret_cast<uint4*>(xg + off + 8192) = lo;
+          for (int i = 0; i < 8; ++i) {
+            const float diff = d - cen_s[col0 + j * 8 + i];
+            // exp(-(d - mu)^2 / gap) = 2^(diff^2 * (-log2(e) / gap))
+            x[i] = tc::ex2_approx(diff * diff * p.rbf_c) * s_in;
           }
+          uint4 hi, lo;
+          tc::split8_f16(x, hi, lo);
+          const uint32_t off = xg + tc::sw64_chunk_offset(row, j);
+          tc::sts128(off, hi);
+          tc::sts128(off + 8192u, lo);
         }
         tc::fence_proxy_async();
         __syncwarp();
@@ -398,53 +405,65 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
       }
       // hidden layers: X <- act(D * 2^s + b) * 2^-s', in place
       for (int l = 0; l < n_hidden; ++l) {
-        tc::mbar_wait(&d_full[g], pd);
-        pd ^= 1;
-        tc::tc_fence_after();
         const float* bl = bias_s + l * 128 + col0;
         const float s_out = p.out_scale[l], s_in = p.in_scale[l + 1];
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          float v[16];
-          tc::tmem_ld16_combined(t_main + col0 + cc * 16, t_corr + col0 + cc * 16, v);
+  #pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        if (g >= n_in_pair) continue;
+          tc::mbar_wait(&d_full[g], pd[g]);
+          pd[g] ^= 1;
+          tc::tc_fence_after();
+          const uint32_t t_main = t_lane + (uint32_t)g * 256u + col0, t_corr = t_main + 128u;
+          const uint32_t xg = xs_a + (uint32_t)g * ETC_X_BYTES + (uint32_t)cq * 16384u;
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            float x[8];
+          for (int cc = 0; cc < 2; ++cc) {
+            float v[16];
+            tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              x[i] = apply_act(fmaf(v[hh * 8 + i], s_out, bl[cc * 16 + hh * 8 + i]), p.act) * s_in;
-            uint4 hi, lo;
-            tc::split8_f16(x, hi, lo);
-            const uint32_t off = (uint32_t)(half * 2 + (cc >> 1)) * 16384u + tc::sw64_chunk_offset(row, (cc & 1) * 2 + hh);
-            *reinterpret_cast<uint4*>(xg + off) = hi;
-            *reinterpret_cast<uint4*>(xg + off + 8192) = lo;
+            for (int hh = 0; hh < 2; ++hh) {
+              float x[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                x[i] = apply_act(fmaf(v[hh * 8 + i], s_out, bl[cc * 16 + hh * 8 + i]), p.act) * s_in;
+              uint4 hi, lo;
+              tc::split8_f16(x, hi, lo);
+              const uint32_t off = xg + tc::sw64_chunk_offset(row, cc * 2 + hh);
+              tc::sts128(off, hi);
+              tc::sts128(off + 8192u, lo);
+            }
           }
+          tc::fence_proxy_async();
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&x_full[g]);
         }
-        tc::fence_proxy_async();
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&x_full[g]);
       }
       // final linear layer (columns 0..15 of the slot's accumulators) * mask
-      tc::mbar_wait(&d_full[g], pd);
-      pd ^= 1;
-      tc::tc_fence_after();
-      if (half == 0) {
-        float va[8], vb[8];
-        tc::tmem_ld8(t_main, va);
-        tc::tmem_ld8(t_corr, vb);
-        if (e < p.n_edges) {
-          const float s_out = p.out_scale[n_hidden];
-          float o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
-          if (p.out != nullptr)
-            for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
-          if (p.rec != nullptr) p.rec[e] = make_float4(o[0], o[1], o[2], __int_as_float(idx));
+      for (int g = 0; g < 2; ++g) {
+        if (g >= n_in_pair) continue;
+        tc::mbar_wait(&d_full[g], pd[g]);
+        pd[g] ^= 1;
+        tc::tc_fence_after();
+        if (cq == 0) {
+          float va[8], vb[8];
+          tc::tmem_ld8(t_lane + (uint32_t)g * 256u, va);
+          tc::tmem_ld8(t_lane + (uint32_t)g * 256u + 128u, vb);
+          const int64_t e = eidx[g];
+          if (e < p.n_edges) {
+            const bool m = dd[g] > 0.0f;
+            const float s_out = p.out_scale[n_hidden];
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
+            if (p.out != nullptr)
+              for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
+            if (p.rec != nullptr) p.rec[e] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+          }
         }
+        tc::tc_fence_before();
       }
-      tc::tc_fence_before();
     }
   }
   tc::tc_fence_before();
@@ -1099,26 +1118,52 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
         }
       }
       // ---- readout: peaks = sum_c (z . Wo[:,c] + bo[c]) * a[c] * std[c] + a[c] * avg[c]; warp per atom,
-      //      skipping classes with a[c] == 0 (exact for finite activations)
-      for (int i = 0; i < 16; ++i) {
-        const int r = we * 16 + i;
-        if (r >= rows) break;
-        const int64_t atom = a0 + r;
-        const float* zr = Z + r * FTC_LDZ;
-        float peak = 0.0f;
-        for (int c = 0; c < p.C; ++c) {
-          const float a = p.atoms[atom * p.C + c];
-          if (a != 0.0f) {
-            float dot = 0.0f;
+      //      skipping classes with a[c] == 0 (exact for finite activations).  The warp's 16 atom rows are
+      //      fetched up front (lane = class, all loads in flight together); classes beyond 32 take the slow loop.
+      {
+        float av[16];
 #pragma unroll
-            for (int k = lane; k < 128; k += 32) dot = fmaf(zr[k], __ldg(p.Wo + k * p.C + c), dot);
+        for (int i = 0; i < 16; ++i) {
+          const int r = we * 16 + i;
+          av[i] = (r < rows && lane < p.C) ? __ldg(p.atoms + (a0 + r) * p.C + lane) : 0.0f;
+        }
+        const float std_l = lane < p.C ? __ldg(p.peak_std + lane) : 0.0f;
+        const float avg_l = lane < p.C ? __ldg(p.peak_avg + lane) : 0.0f;
+        const float bo_l = lane < p.C ? __ldg(p.bo + lane) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int r = we * 16 + i;
+          if (r >= rows) continue;               // warp-uniform
+          const float* zr = Z + r * FTC_LDZ;
+          const float4 z4 = *reinterpret_cast<const float4*>(zr + lane * 4);   // this lane's 4 features
+          float peak = 0.0f;
+          unsigned nzmask = __ballot_sync(0xffffffffu, av[i] != 0.0f);
+          while (nzmask) {
+            const int c = __ffs(nzmask) - 1;
+            nzmask &= nzmask - 1;
+            const float* wo = p.Wo + (lane * 4) * p.C + c;
+            float dot = z4.x * __ldg(wo);
+            dot = fmaf(z4.y, __ldg(wo + p.C), dot);
+            dot = fmaf(z4.z, __ldg(wo + 2 * p.C), dot);
+            dot = fmaf(z4.w, __ldg(wo + 3 * p.C), dot);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            const float full = dot + p.bo[c];
-            peak += full * a * p.peak_std[c] + a * p.peak_avg[c];
+            const float a = __shfl_sync(0xffffffffu, av[i], c);
+            const float full = dot + __shfl_sync(0xffffffffu, bo_l, c);
+            peak += full * a * __shfl_sync(0xffffffffu, std_l, c) + a * __shfl_sync(0xffffffffu, avg_l, c);
           }
+          for (int c = 32; c < p.C; ++c) {       // (num_elem > 32 only)
+            const float a = p.atoms[(a0 + r) * p.C + c];
+            if (a != 0.0f) {
+              float dot = 0.0f;
+              for (int k = lane; k < 128; k += 32) dot = fmaf(zr[k], __ldg(p.Wo + k * p.C + c), dot);
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+              peak += (dot + p.bo[c]) * a * p.peak_std[c] + a * p.peak_avg[c];
+            }
+          }
+          if (lane == 0) p.peaks[a0 + r] = peak;
         }
-        if (lane == 0) p.peaks[atom] = peak;
       }
     }
   }
