@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int q = 0; q < MTC_PASSES * E; ++q, ++it) {
           const uint32_t slot = it % MTC_BRING, ph = (it / MTC_BRING) & 1;
-          tc::mbar_wait(&b_empty[slot], ph ^ 1);
+          tc::mbar_wait_relaxed(&b_empty[slot], ph ^ 1);
           tc::mbar_expect_tx(&b_full[slot], 32768);
           tc::bulk_g2s(b_ring + slot * 32768, p.Wimg + (size_t)q * 32768, 32768, &b_full[slot]);
         }
@@ -618,7 +618,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
         const int64_t a0 = tile * 128;
         const int rows = (int)min((int64_t)128, p.n_atoms - a0);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 16u;
-        tc::mbar_wait(rec_empty, (t & 1) ^ 1);
+        tc::mbar_wait_relaxed(rec_empty, (t & 1) ^ 1);
         tc::mbar_expect_tx(rec_full, bytes);
         tc::bulk_g2s(rec_s, p.rec + a0 * K, bytes, rec_full);
       }
@@ -739,26 +739,31 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       // 8 independent row loads of half-step (row, half) at feature pass ps
       // (no branches around the loads: a branch makes the compiler drain every outstanding load first;
       //  out-of-range rows / slots read an in-bounds shared address and are neutralised by selects)
-      auto issue = [&](float4 (&hv)[8], int row, int half, int ps) {
+      // FULL = full tile and K == 16: no range predicates at all
+      const bool full = rows == 128 && K == 16;
+      auto issue = [&](float4 (&hv)[8], int row, int half, int ps, bool FULL) {
         const bool rv = row < rows;
         const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u + 12u;
+        const float* hp = hq + ps * 32;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           uint32_t idx = tc::lds32(ra + u * 16);
-          idx = (rv && half * 8 + u < K) ? idx : 0u;
-          hv[u] = tc::ldg128(hq + (size_t)idx * 256 + ps * 32);
+          if (!FULL) idx = (rv && half * 8 + u < K) ? idx : 0u;
+          hv[u] = tc::ldg128(hp + (size_t)idx * 256);
         }
       };
-      auto consume = [&](const float4 (&hv)[8], int row, int half, float (&acc)[3][4]) {
+      auto consume = [&](const float4 (&hv)[8], int row, int half, float (&acc)[3][4], bool FULL) {
         const bool rv = row < rows;
         const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           float4 r = tc::lds128(ra + u * 16);
-          const bool ok = rv && half * 8 + u < K;
-          r.x = ok ? r.x : 0.0f;
-          r.y = ok ? r.y : 0.0f;
-          r.z = ok ? r.z : 0.0f;
+          if (!FULL) {
+            const bool ok = rv && half * 8 + u < K;
+            r.x = ok ? r.x : 0.0f;
+            r.y = ok ? r.y : 0.0f;
+            r.z = ok ? r.z : 0.0f;
+          }
           acc[0][0] = fmaf(r.x, hv[u].x, acc[0][0]);
           acc[0][1] = fmaf(r.x, hv[u].y, acc[0][1]);
           acc[0][2] = fmaf(r.x, hv[u].z, acc[0][2]);
@@ -775,7 +780,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       };
 
       float4 hvA[8], hvB[8];
-      issue(hvA, pw * 4 + rsub, 0, 0);       // first half-step of the tile, in flight during the scale pass
+      issue(hvA, pw * 4 + rsub, 0, 0, false);   // first half-step of the tile, in flight during the scale pass
 
       // per-row bound |T[i,.]| <= sum_j max_n|e_ijn| * hmax[nl_ij]  ->  power-of-two scale
       {
@@ -813,16 +818,21 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           for (int n = 0; n < 3; ++n)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
-          issue(hvB, row, 1, ps);
-          consume(hvA, row, 0, acc);
-          {
-            // next half-step: next row group of this pass, or the first one of the next pass
-            const bool last = step == 3;
-            const int nrow = last ? pw * 4 + rsub : row + 32;
-            const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);   // (the tile's very last prefetch is unused)
-            issue(hvA, nrow, 0, nps);
+          // next half-step: next row group of this pass, or the first one of the next pass
+          const bool last = step == 3;
+          const int nrow = last ? pw * 4 + rsub : row + 32;
+          const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);   // (the tile's very last prefetch is unused)
+          if (full) {
+            issue(hvB, row, 1, ps, true);
+            consume(hvA, row, 0, acc, true);
+            issue(hvA, nrow, 0, nps, true);
+            consume(hvB, row, 1, acc, true);
+          } else {
+            issue(hvB, row, 1, ps, false);
+            consume(hvA, row, 0, acc, false);
+            issue(hvA, nrow, 0, nps, false);
+            consume(hvB, row, 1, acc, false);
           }
-          consume(hvB, row, 1, acc);
           const float sc = fs[row];
           const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
                                (((uint32_t)q8 & 1u) << 3);

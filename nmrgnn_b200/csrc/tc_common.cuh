@@ -34,29 +34,65 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait suspends the warp in hardware until the phase completes or an implementation-defined time
+// limit expires.  HINT_NS > 0 passes an explicit suspend-time hint: used by the loader threads, which
+// run far ahead of their consumers and would otherwise burn issue slots of the working warps.
+template <uint32_t HINT_NS>
+__device__ __forceinline__ bool mbar_try_wait_t(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
+  if (HINT_NS == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(HINT_NS)
+        : "memory");
+  }
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_t<0>(bar, parity); }
 // Bounded wait: a protocol bug must trap (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+template <uint32_t HINT_NS>
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_t<HINT_NS>(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_t<HINT_NS>(bar, parity)) {
+    __nanosleep(HINT_NS ? 256 : 40);       // back off: polling warps must not take issue slots from working warps
+    if ((++spins & 255u) == 0u) {          // look at the clock only every 256 polls
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) {  // ~4 s at 2 GHz
+        printf("nmrgnn_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+               threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
+    }
+  }
+}
+// (the latency-critical form polls with a clock read per iteration: measured faster on the edge kernel
+//  than back-to-back polls, nanosleep back-off or a suspend hint)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s at 2 GHz
       printf("nmrgnn_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
 }
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_t<4000>(bar, parity); }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
