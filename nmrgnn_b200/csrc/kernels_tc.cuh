@@ -611,16 +611,30 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
         }
     }
   } else if (warp == 2) {
-    // ===================== edge-record loader =====================
-    if (lane == 0) {
-      uint32_t t = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    // ===================== edge-record loader + L2 prefetcher =====================
+    // After handing tile t's records to the producers, the warp pulls the CTA's NEXT tile into L2: its
+    // edge records and the node rows of its own atom range (for chain-ordered molecules that is where
+    // most neighbours live), so that the gathers of the next tile hit L2 instead of paying DRAM latency
+    // on the producers' critical path.  Pure hint: no effect on results.
+    uint32_t t = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      if (lane == 0) {
         const int64_t a0 = tile * 128;
         const int rows = (int)min((int64_t)128, p.n_atoms - a0);
         const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 16u;
         tc::mbar_wait_relaxed(rec_empty, (t & 1) ^ 1);
         tc::mbar_expect_tx(rec_full, bytes);
         tc::bulk_g2s(rec_s, p.rec + a0 * K, bytes, rec_full);
+      }
+      __syncwarp();
+      const int64_t nt = tile + gridDim.x;
+      if (nt < n_tiles) {
+        const int64_t b0 = nt * 128;
+        const int nrows = (int)min((int64_t)128, p.n_atoms - b0);
+        const char* hb = reinterpret_cast<const char*>(p.h_in + b0 * 256);
+        for (int i = lane; i < nrows * 8; i += 32) tc::prefetch_l2(hb + (size_t)i * 128);
+        const char* rb = reinterpret_cast<const char*>(p.rec + b0 * K);
+        for (int i = lane; i * 128 < nrows * K * 16; i += 32) tc::prefetch_l2(rb + (size_t)i * 128);
       }
     }
   } else if (warp == 1) {
@@ -661,63 +675,97 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       }
     }
   } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue: thread = atom row =====================
+    // ===================== epilogue =====================
+    // TMEM hands every thread one atom row; global memory wants 128 contiguous bytes per row and
+    // instruction.  Each group of 8 lanes therefore transposes its 8 rows x 8 float4 block with
+    // shuffles: afterwards lane i of the group holds the i-th 16 bytes of all 8 rows, so that the residual
+    // loads and the stores of h_out cover full 128-byte lines (4 L1 wavefronts per instruction, not 32).
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int gi = lane & 7;                       // position inside the 8-lane group = float4 chunk after transposition
+    const int grow = q * 32 + (lane & 24);         // first row of the group
     const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_corr = t_main + 256u;
     uint32_t t = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const int64_t a0 = tile * 128;
       const int rows = (int)min((int64_t)128, p.n_atoms - a0);
-      const bool valid = row < rows;
-      const int64_t atom = valid ? a0 + row : a0;        // invalid rows read a valid address, write nothing
-      const float* hin = p.h_in + atom * 256;
-      float* hout = p.h_out + atom * 256;
-      // the residual row is prefetched one 16-column group ahead of the accumulator reads
-      float4 res[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) res[j] = tc::ldg128(hin + j * 4);
       tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
       const float osc = oscale[(t & 1) * 128 + row];
+      // rows grow .. grow+7 of this group, clamped for the loads (stores are predicated)
+      const float* hin = p.h_in + (a0 + min(grow, rows - 1)) * 256 + gi * 4;
+      float* hout = p.h_out + (a0 + grow) * 256 + gi * 4;
+      // (rows past the end of a partial tile re-read the tile's last row; their stores are predicated off)
+      const int rlast = rows - 1 - min(grow, rows - 1);
+      float4 res[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) res[k] = p.raw ? make_float4(0.f, 0.f, 0.f, 0.f) : tc::ldg128(hin + min(k, rlast) * 256);
       tc::mbar_wait(d_full, t & 1);
       tc::tc_fence_after();
-      float hm = 0.0f;
+      float hm[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hm[k] = 0.0f;
 #pragma unroll 1
-      for (int cc = 0; cc < 16; ++cc) {
-        float v[16];
-        tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
-        float4 cur[4];
+      for (int cc = 0; cc < 8; ++cc) {
+        float4 x[8];
+        {
+          float v[16];
+          tc::tmem_ld16_combined(t_main + cc * 32, t_corr + cc * 32, v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cur[j] = res[j];
-        if (cc + 1 < 16) {
+          for (int j = 0; j < 4; ++j) x[j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
+          tc::tmem_ld16_combined(t_main + cc * 32 + 16, t_corr + cc * 32 + 16, v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) res[j] = tc::ldg128(hin + (cc + 1) * 16 + j * 4);
+          for (int j = 0; j < 4; ++j) x[4 + j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
         }
-        if (valid) {
+        // 8 x 8 transpose of float4 inside the 8-lane group (3 butterfly stages)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4 o;
-            if (p.raw) {
-              o.x = v[j * 4 + 0] * osc;
-              o.y = v[j * 4 + 1] * osc;
-              o.z = v[j * 4 + 2] * osc;
-              o.w = v[j * 4 + 3] * osc;
-            } else {
-              o.x = apply_act(v[j * 4 + 0] * osc, p.act) + cur[j].x;
-              o.y = apply_act(v[j * 4 + 1] * osc, p.act) + cur[j].y;
-              o.z = apply_act(v[j * 4 + 2] * osc, p.act) + cur[j].z;
-              o.w = apply_act(v[j * 4 + 3] * osc, p.act) + cur[j].w;
-            }
-            hm = fmaxf(hm, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-            *reinterpret_cast<float4*>(hout + cc * 16 + j * 4) = o;
+        for (int m = 1; m < 8; m <<= 1) {
+          const bool up = (lane & m) != 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j & m) continue;
+            const float4 lo4 = x[j], hi4 = x[j | m];
+            float4 snd = up ? lo4 : hi4, rcv;
+            rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m);
+            rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
+            rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m);
+            rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
+            x[j] = up ? rcv : lo4;
+            x[j | m] = up ? hi4 : rcv;
           }
+        }
+        // now x[k] = columns cc*32 + gi*4 .. +3 of row grow + k
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float4 o;
+          if (p.raw) {
+            o = x[k];
+          } else {
+            o.x = apply_act(x[k].x, p.act) + res[k].x;
+            o.y = apply_act(x[k].y, p.act) + res[k].y;
+            o.z = apply_act(x[k].z, p.act) + res[k].z;
+            o.w = apply_act(x[k].w, p.act) + res[k].w;
+          }
+          hm[k] = fmaxf(hm[k], fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          if (grow + k < rows) *reinterpret_cast<float4*>(hout + k * 256 + cc * 32) = o;
+          // the residual of the next 32 columns is in flight during the next accumulator read + transposition
+          if (cc + 1 < 8 && !p.raw) res[k] = tc::ldg128(hin + min(k, rlast) * 256 + (cc + 1) * 32);
         }
       }
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(d_empty);
-      if (valid) p.hmax_out[atom] = hm;
+      // row maxima: reduce over the 8 lanes of the group, lane k writes row grow + k
+      float mine = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = hm[k];
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+        v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+        if (gi == k) mine = v;
+      }
+      if (grow + gi < rows) p.hmax_out[a0 + grow + gi] = mine;
     }
   } else if (warp >= 8) {
     // ===================== producers: gather-aggregate, scale, split =====================
@@ -734,6 +782,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       const int rows = (int)min((int64_t)128, p.n_atoms - a0);
       float* fs = fscale + (t & 1) * 128;
       float* os = oscale + (t & 1) * 128;
+      const uint32_t fs_a = tc::smem_u32(fs);
       tc::mbar_wait(rec_full, t & 1);
 
       // 8 independent row loads of half-step (row, half) at feature pass ps
@@ -818,6 +867,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           for (int n = 0; n < 3; ++n)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
+          const float sc = tc::lds32f(fs_a + (uint32_t)row * 4u);   // needed only after the FMAs: latency hidden
           // next half-step: next row group of this pass, or the first one of the next pass
           const bool last = step == 3;
           const int nrow = last ? pw * 4 + rsub : row + 32;
@@ -833,7 +883,6 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
             issue(hvA, nrow, 0, nps, false);
             consume(hvB, row, 1, acc, false);
           }
-          const float sc = fs[row];
           const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
                                (((uint32_t)q8 & 1u) << 3);
 #pragma unroll
