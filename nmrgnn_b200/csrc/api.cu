@@ -78,6 +78,7 @@ struct nmrgnn_handle {
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
   bool compensate = true;
+  long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 4096;          // calls smaller than this run on the exact-FP32 kernels (one wave either way)
 };
 
@@ -447,6 +448,7 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.act = h->d.mp_activation;
   a.corr = (h->compensate && !raw) ? h->mp_corr[layer] : 1.0f;
   a.raw = raw;
+  a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
   mp_layer_tc_kernel<<<grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s>>>(a);
   h->launches++;
@@ -1114,6 +1116,31 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "force_ffma") == 0) {
     h->force_ffma = value != 0;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_role_counters") == 0) {
+    // value != 0: allocate / zero the per-CTA role counters and print their means on value == 2
+    if (value && !h->mp_dbg) {
+      CUDA_TRY(h, cudaMalloc(&h->mp_dbg, 1024 * 8 * sizeof(long long)));
+      h->owned.push_back((float*)h->mp_dbg);
+    }
+    if (value == 1) CUDA_TRY(h, cudaMemset(h->mp_dbg, 0, 1024 * 8 * sizeof(long long)));
+    if (value == 2 && h->mp_dbg) {
+      std::vector<long long> c(1024 * 8);
+      CUDA_TRY(h, cudaMemcpy(c.data(), h->mp_dbg, c.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double m[8] = {0};
+      int n = 0;
+      for (int b = 0; b < h->num_sms; ++b)
+        if (c[b * 8] > 0) {
+          ++n;
+          for (int i = 0; i < 8; ++i) m[i] += (double)c[b * 8 + i];
+        }
+      if (n)
+        printf("mp roles (mean cycles per CTA over %d CTAs): mma total %.0f | mma waits: epilogue %.0f producers %.0f W' %.0f | "
+               "epilogue busy %.0f | producer waits: a_empty %.0f rec %.0f\n",
+               n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[5] / n, m[6] / n);
+    }
+    if (value == 0) h->mp_dbg = nullptr;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "tc_min_atoms") == 0) {

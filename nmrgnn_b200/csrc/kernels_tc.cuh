@@ -543,6 +543,7 @@ struct MpTcArgs {
   int act;
   float corr;                // 1 + c: compensates the round-toward-zero accumulation of tcgen05
   int raw;                   // 1: h_out = inv_degree * D (no activation, no residual) -- calibration tap
+  long long* dbg;            // optional [gridDim][8] cycle counters (diagnostics): see tools/diag_mp_roles.py
 };
 
 constexpr int MTC_THREADS = 512;
@@ -643,16 +644,24 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       const uint32_t idesc = tc::make_idesc_f16(128, 256);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
       uint32_t it = 0, pass = 0, t = 0;
+      long long w_d = 0, w_a = 0, w_b = 0, c0 = 0;
+      const long long k0 = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        if (p.dbg) c0 = clock64();
         tc::mbar_wait(d_empty, (t & 1) ^ 1);      // epilogue has drained the previous tile's accumulators
+        if (p.dbg) w_d += clock64() - c0;
         tc::tc_fence_after();
         for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
           const uint32_t st = pass & 1;
+          if (p.dbg) c0 = clock64();
           tc::mbar_wait(&a_full[st], (pass >> 1) & 1);
+          if (p.dbg) w_a += clock64() - c0;
           tc::tc_fence_after();
           for (int n = 0; n < E; ++n, ++it) {
             const uint32_t slot = it % MTC_BRING;
+            if (p.dbg) c0 = clock64();
             tc::mbar_wait(&b_full[slot], (it / MTC_BRING) & 1);
+            if (p.dbg) w_b += clock64() - c0;
             tc::tc_fence_after();
             const uint8_t* ac = a_st + (st * 3 + n) * 16384;
             const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(ac));
@@ -672,6 +681,13 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           tc::umma_commit(&a_empty[st]);
         }
         tc::umma_commit(d_full);
+      }
+      if (p.dbg) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - k0;   // MMA thread: total
+        o[1] = w_d;              //   waiting for the epilogue (d_empty)
+        o[2] = w_a;              //   waiting for the producers (a_full)
+        o[3] = w_b;              //   waiting for W' (b_full)
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -701,6 +717,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
 #pragma unroll
       for (int k = 0; k < 8; ++k) res[k] = p.raw ? make_float4(0.f, 0.f, 0.f, 0.f) : tc::ldg128(hin + min(k, rlast) * 256);
       tc::mbar_wait(d_full, t & 1);
+      const long long e0 = p.dbg ? clock64() : 0;
       tc::tc_fence_after();
       float hm[8];
 #pragma unroll
@@ -755,6 +772,7 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(d_empty);
+      if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
       // row maxima: reduce over the 8 lanes of the group, lane k writes row grow + k
       float mine = 0.0f;
 #pragma unroll
@@ -783,23 +801,32 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       float* fs = fscale + (t & 1) * 128;
       float* os = oscale + (t & 1) * 128;
       const uint32_t fs_a = tc::smem_u32(fs);
+      const long long r0c = p.dbg ? clock64() : 0;
       tc::mbar_wait(rec_full, t & 1);
+      if (p.dbg && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 6), (unsigned long long)(clock64() - r0c));
 
       // 8 independent row loads of half-step (row, half) at feature pass ps
       // (no branches around the loads: a branch makes the compiler drain every outstanding load first;
       //  out-of-range rows / slots read an in-bounds shared address and are neutralised by selects)
       // FULL = full tile and K == 16: no range predicates at all
       const bool full = rows == 128 && K == 16;
-      auto issue = [&](float4 (&hv)[8], int row, int half, int ps, bool FULL) {
+      // neighbour indices are fetched one half-step ahead of the row loads that use them (`nidx`), so the
+      // address computation never waits for shared memory
+      uint32_t nidx[8];
+      auto load_idx = [&](int row, int half, bool FULL) {
         const bool rv = row < rows;
         const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u + 12u;
-        const float* hp = hq + ps * 32;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           uint32_t idx = tc::lds32(ra + u * 16);
           if (!FULL) idx = (rv && half * 8 + u < K) ? idx : 0u;
-          hv[u] = tc::ldg128(hp + (size_t)idx * 256);
+          nidx[u] = idx;
         }
+      };
+      auto issue = [&](float4 (&hv)[8], int ps) {
+        const float* hp = hq + ps * 32;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) hv[u] = tc::ldg128(hp + (size_t)nidx[u] * 256);
       };
       auto consume = [&](const float4 (&hv)[8], int row, int half, float (&acc)[3][4], bool FULL) {
         const bool rv = row < rows;
@@ -829,7 +856,9 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       };
 
       float4 hvA[8], hvB[8];
-      issue(hvA, pw * 4 + rsub, 0, 0, false);   // first half-step of the tile, in flight during the scale pass
+      load_idx(pw * 4 + rsub, 0, false);
+      issue(hvA, 0);                            // first half-step of the tile, in flight during the scale pass
+      load_idx(pw * 4 + rsub, 1, false);
 
       // per-row bound |T[i,.]| <= sum_j max_n|e_ijn| * hmax[nl_ij]  ->  power-of-two scale
       {
@@ -857,7 +886,9 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
 
       for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
         const uint32_t st = pass & 1;
+        const long long p0 = p.dbg ? clock64() : 0;
         tc::mbar_wait(&a_empty[st], ((pass >> 1) & 1) ^ 1);
+        if (p.dbg && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 5), (unsigned long long)(clock64() - p0));
         const uint32_t ab = ast_a + st * 3 * 16384;
 #pragma unroll 1
         for (int step = 0; step < 4; ++step) {
@@ -872,15 +903,20 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           const bool last = step == 3;
           const int nrow = last ? pw * 4 + rsub : row + 32;
           const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);   // (the tile's very last prefetch is unused)
+          // entering: hvA holds (row, half 0) in flight, nidx the indices of (row, half 1)
           if (full) {
-            issue(hvB, row, 1, ps, true);
+            issue(hvB, ps);
+            load_idx(nrow, 0, true);
             consume(hvA, row, 0, acc, true);
-            issue(hvA, nrow, 0, nps, true);
+            issue(hvA, nps);
+            load_idx(nrow, 1, true);
             consume(hvB, row, 1, acc, true);
           } else {
-            issue(hvB, row, 1, ps, false);
+            issue(hvB, ps);
+            load_idx(nrow, 0, false);
             consume(hvA, row, 0, acc, false);
-            issue(hvA, nrow, 0, nps, false);
+            issue(hvA, nps);
+            load_idx(nrow, 1, false);
             consume(hvB, row, 1, acc, false);
           }
           const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
