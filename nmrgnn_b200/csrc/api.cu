@@ -35,6 +35,8 @@ struct nmrgnn_handle {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // host-buffer calls: H2D of later chunks overlaps the edge kernel of earlier ones
+  cudaEvent_t ev_copy[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::string err;
   std::string path = "ffma";
   int64_t launches = 0;
@@ -642,6 +644,9 @@ void nmrgnn_destroy(nmrgnn_handle* h) {
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->err_flag) cudaFree(h->err_flag);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
+  for (cudaEvent_t e : h->ev_copy)
+    if (e) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -695,6 +700,8 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
 
   CUDA_RC(cudaSetDevice(device));
   CUDA_RC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_RC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->ev_copy) CUDA_RC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CUDA_RC(cudaMalloc(&h->err_flag, sizeof(int)));
   CUDA_RC(cudaMemset(h->err_flag, 0, sizeof(int)));
   CUDA_RC(cudaMallocHost(&h->err_flag_host, sizeof(int)));
@@ -1004,10 +1011,47 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
   const size_t C = h->d.num_elem, F = h->d.atom_features, E = h->d.edge_features;
   const void *d_atoms, *d_nl, *d_edges, *d_inv;
   void* d_peaks;
+  // Host buffers, large call: the inputs go up on a second stream in chunks (edges + nlist first, in atom
+  // ranges aligned to the 128-edge tiles), each chunk's edge kernel starts as soon as its copy has landed,
+  // atoms / inv_degree follow while the edge kernels run.  Chunk c is guarded by ev_copy[c], the rest by [8].
+  struct CopyGuard {   // an early error return must not leave uploads from the caller's buffers in flight
+    cudaStream_t cs = nullptr;
+    ~CopyGuard() {
+      if (cs) cudaStreamSynchronize(cs);
+    }
+  } copy_guard;
+  constexpr int MAX_CHUNKS = 8;
+  int n_chunks = 1;
+  int64_t chunk_atoms = n_atoms;
+  if (mem == NMRGNN_MEM_HOST && n_atoms >= 32768) {
+    n_chunks = 4;
+    chunk_atoms = (((n_atoms + n_chunks - 1) / n_chunks) + 127) / 128 * 128;
+    n_chunks = (int)((n_atoms + chunk_atoms - 1) / chunk_atoms);
+    if (n_chunks > MAX_CHUNKS) n_chunks = MAX_CHUNKS, chunk_atoms = n_atoms;
+  }
+  if (n_chunks > 1) {
+    if ((rc = ensure(h, h->atoms, n_atoms * C * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->nlist, n_atoms * k * sizeof(int32_t)))) return rc;
+    if ((rc = ensure(h, h->edges, n_atoms * k * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->invdeg, n_atoms * sizeof(float)))) return rc;
+    d_atoms = h->atoms.p, d_nl = h->nlist.p, d_edges = h->edges.p, d_inv = h->invdeg.p;
+    cudaStream_t cs = h->copy_stream;
+    copy_guard.cs = cs;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t a0 = c * chunk_atoms, na = std::min<int64_t>(chunk_atoms, n_atoms - a0);
+      CUDA_TRY(h, cudaMemcpyAsync((float*)h->edges.p + a0 * k, edges + a0 * k, na * k * sizeof(float), cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(h, cudaMemcpyAsync((int32_t*)h->nlist.p + a0 * k, nlist + a0 * k, na * k * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+      CUDA_TRY(h, cudaEventRecord(h->ev_copy[c], cs));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->atoms.p, atoms, n_atoms * C * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(h, cudaMemcpyAsync(h->invdeg.p, inv_degree, n_atoms * sizeof(float), cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(h, cudaEventRecord(h->ev_copy[8], cs));
+  } else {
   if ((rc = io.in(atoms, n_atoms * C * sizeof(float), h->atoms, &d_atoms))) return rc;
   if ((rc = io.in(nlist, n_atoms * k * sizeof(int32_t), h->nlist, &d_nl))) return rc;
   if ((rc = io.in(edges, n_atoms * k * sizeof(float), h->edges, &d_edges))) return rc;
   if ((rc = io.in(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;
+  }
   if ((rc = io.out_buf(peaks, n_atoms * sizeof(float), h->peaks, &d_peaks))) return rc;
   if ((rc = ensure(h, h->efeat, n_atoms * k * E * sizeof(float)))) return rc;
   if ((rc = ensure(h, h->hA, n_atoms * F * sizeof(float)))) return rc;
@@ -1033,9 +1077,15 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
     float4* rec = (float4*)h->rec.p;
     float* ma = (float*)h->hmaxA.p;
     float* mb = (float*)h->hmaxB.p;
-    if ((rc = launch_edge(h, s, (const float*)d_edges, n_atoms * k, nullptr, (const int32_t*)d_nl, n_atoms, rec)))
-      return rc;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t a0 = c * chunk_atoms, na = std::min<int64_t>(chunk_atoms, n_atoms - a0);
+      if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[c], 0));
+      if ((rc = launch_edge(h, s, (const float*)d_edges + a0 * k, na * k, nullptr, (const int32_t*)d_nl + a0 * k, n_atoms,
+                            rec + a0 * k)))
+        return rc;
+    }
     mark();
+    if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[8], 0));
     if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
     if ((rc = launch_absmax(h, s, ha, n_atoms, ma))) return rc;
     mark();
@@ -1046,8 +1096,14 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
       std::swap(ma, mb);
     }
   } else {
-    if ((rc = launch_edge(h, s, (const float*)d_edges, n_atoms * k, ef, (const int32_t*)d_nl, n_atoms))) return rc;
+    for (int c = 0; c < n_chunks; ++c) {
+      const int64_t a0 = c * chunk_atoms, na = std::min<int64_t>(chunk_atoms, n_atoms - a0);
+      if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[c], 0));
+      if ((rc = launch_edge(h, s, (const float*)d_edges + a0 * k, na * k, ef + a0 * k * E, (const int32_t*)d_nl + a0 * k, n_atoms)))
+        return rc;
+    }
     mark();
+    if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[8], 0));
     if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
     mark();
     for (int l = 0; l < h->d.n_mp; ++l) {
