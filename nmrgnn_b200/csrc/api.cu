@@ -359,9 +359,16 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
   return NMRGNN_OK;
 }
 
-int launch_embed(nmrgnn_handle* h, cudaStream_t s, const float* atoms, int64_t n, float* nodes) {
+int launch_embed(nmrgnn_handle* h, cudaStream_t s, const float* atoms, int64_t n, float* nodes, float* hmax = nullptr) {
   if (n == 0) return NMRGNN_OK;
   const int C = h->d.num_elem, F = h->d.atom_features;
+  if (F == 256 && (size_t)EMBED256_ATOMS * C * sizeof(float) <= 40 * 1024) {
+    const int64_t blocks = (n + EMBED256_ATOMS - 1) / EMBED256_ATOMS;
+    embed256_kernel<<<(unsigned)blocks, 256, EMBED256_ATOMS * C * sizeof(float), s>>>(atoms, h->embed, nodes, hmax, n, C);
+    h->launches++;
+    return NMRGNN_OK;
+  }
+  if (hmax != nullptr) return fail(h, NMRGNN_ERR_BAD_DIMS, "fused row maximum needs F = 256");
   const int64_t blocks = (n + EMBED_ATOMS - 1) / EMBED_ATOMS;
   embed_kernel<<<(unsigned)blocks, 256, EMBED_ATOMS * C * sizeof(float), s>>>(atoms, h->embed, nodes, n, C, F);
   h->launches++;
@@ -1086,8 +1093,7 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
     }
     mark();
     if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[8], 0));
-    if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha))) return rc;
-    if ((rc = launch_absmax(h, s, ha, n_atoms, ma))) return rc;
+    if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha, ma))) return rc;
     mark();
     for (int l = 0; l < h->d.n_mp; ++l) {
       if ((rc = launch_mp_tc(h, s, l, ha, ma, rec, (const float*)d_inv, n_atoms, k, hb, mb))) return rc;

@@ -164,6 +164,47 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ at
   }
 }
 
+// F = 256 variant used by the forward: 32 atoms per block, 16-byte stores (thread = 4 features of 8 atoms),
+// and the per-atom max |h| that the tensor-core MP layer needs for its fp16 range scaling, written in the
+// same pass (hmax may be null).
+constexpr int EMBED256_ATOMS = 32;
+__global__ void __launch_bounds__(256) embed256_kernel(const float* __restrict__ atoms, const float* __restrict__ We,
+                                                       float* __restrict__ nodes, float* __restrict__ hmax,
+                                                       int64_t n_atoms, int C) {
+  extern __shared__ __align__(16) float a_s[];  // [EMBED256_ATOMS][C]
+  __shared__ float m_s[EMBED256_ATOMS][2];
+  const int64_t i0 = (int64_t)blockIdx.x * EMBED256_ATOMS;
+  const int n_here = (int)min((int64_t)EMBED256_ATOMS, n_atoms - i0);
+  for (int i = threadIdx.x; i < EMBED256_ATOMS * C; i += 256) a_s[i] = i < n_here * C ? atoms[i0 * C + i] : 0.0f;
+  __syncthreads();
+  const int cg = threadIdx.x & 63, sub = threadIdx.x >> 6;     // 4 features cg*4.., atoms sub, sub+4, ...
+  float4 acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = 0; c < C; ++c) {
+    const float4 w = *reinterpret_cast<const float4*>(We + c * 256 + cg * 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = a_s[(sub + 4 * i) * C + c];
+      acc[i].x = fmaf(a, w.x, acc[i].x);
+      acc[i].y = fmaf(a, w.y, acc[i].y);
+      acc[i].z = fmaf(a, w.z, acc[i].z);
+      acc[i].w = fmaf(a, w.w, acc[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = sub + 4 * i;
+    if (r < n_here) *reinterpret_cast<float4*>(nodes + (i0 + r) * 256 + cg * 4) = acc[i];
+    float m = fmaxf(fmaxf(fabsf(acc[i].x), fabsf(acc[i].y)), fmaxf(fabsf(acc[i].z), fabsf(acc[i].w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) m_s[r][(threadIdx.x >> 5) & 1] = m;   // the row's 64 threads are 2 warps
+  }
+  __syncthreads();
+  if (hmax != nullptr && threadIdx.x < n_here) hmax[i0 + threadIdx.x] = fmaxf(m_s[threadIdx.x][0], m_s[threadIdx.x][1]);
+}
+
 // ----------------------------------------------------------------------------------
 // MP layer, F = 256.  One CTA = 128 atoms.  For each 32-feature slice of the input
 // nodes the warps gather-aggregate T[i,(n,l)] = sum_j e[i,j,n] h[nl[i,j],l] into

@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
       }
       // hidden layers: X <- act(D * 2^s + b) * 2^-s', in place
       for (int l = 0; l < n_hidden; ++l) {
-        const float* bl = bias_s + l * 128 + col0;
+        const uint32_t bl_a = tc::smem_u32(bias_s + l * 128 + col0);
         const float s_out = p.out_scale[l], s_in = p.in_scale[l + 1];
   #pragma unroll
       for (int g = 0; g < 2; ++g) {
@@ -418,13 +418,16 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             float v[16];
+            // (explicit shared loads: a pointer carved out of the aligned buffer would compile to generic loads)
             tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
+              const float4 b0 = tc::lds128(bl_a + cc * 64 + hh * 32), b1 = tc::lds128(bl_a + cc * 64 + hh * 32 + 16);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float x[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                x[i] = apply_act(fmaf(v[hh * 8 + i], s_out, bl[cc * 16 + hh * 8 + i]), p.act) * s_in;
+                x[i] = apply_act(fmaf(v[hh * 8 + i], s_out, bb[i]), p.act) * s_in;
               uint4 hi, lo;
               tc::split8_f16(x, hi, lo);
               const uint32_t off = xg + tc::sw64_chunk_offset(row, cc * 2 + hh);
