@@ -958,14 +958,14 @@ namespace nmr {
 // The node tile X lives in shared memory as the fp16x3 A operand (hi | lo, 8 K-chunks of
 // 32 features); every residual layer X <- act(X W + b) + X is
 //   MMA:      D[128 x 256] = X * W     two N = 128 halves per K-chunk, main / corr accumulators in TMEM
-//   epilogue: thread = (atom row, 128-column half): D -> RZ compensation -> bias -> act -> + x_old
+//   epilogue: thread = (atom row, 64-column quarter): D -> RZ compensation -> bias -> act -> + x_old
 //             (x_old is re-assembled from the hi/lo pair it is about to overwrite: 22 mantissa bits,
 //              round-to-nearest) -> split -> written back in place as the next layer's operand.
 // The last layer (256 -> 128, no residual) leaves Z in fp32 in shared memory (overlaying X, whose
 // MMAs have completed) for the warp-per-atom readout.  W streams through a ring of 16 KB bulk
 // copies (one K-chunk x one N-half).  Rows are pre-scaled by a power of two from an a-priori
 // affine bound of |x| per layer (fp16 range); the scale is exact to undo.
-//   warp 0: W loader   warp 1: MMA issuer + TMEM owner   warps 2-9: load / epilogue / readout
+//   warp 0: W loader   warp 1: MMA issuer + TMEM owner   warps 2-17: load / epilogue / readout
 // ----------------------------------------------------------------------------------
 struct FcTcArgs {
   const float* nodes;        // [n_atoms, 256]
@@ -987,7 +987,7 @@ struct FcTcArgs {
   const float* peak_avg;     // [C]
 };
 
-constexpr int FTC_THREADS = 320;
+constexpr int FTC_THREADS = 576;
 constexpr int FTC_RING = 5;
 constexpr int FTC_LDZ = 132;
 constexpr size_t FTC_X_BYTES = 8 * 16384;
@@ -1015,7 +1015,7 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
       tc::mbar_init(&w_full[i], 1);
       tc::mbar_init(&w_empty[i], 1);
     }
-    tc::mbar_init(x_full, 8);
+    tc::mbar_init(x_full, 16);
     tc::mbar_init(d_full, 1);
     tc::mbar_fence_init();
   }
@@ -1079,13 +1079,13 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
         }
     }
   } else {
-    // ===================== load / epilogue / readout warps =====================
-    const int we = warp - 2;                 // 0..7
+    // ===================== load / epilogue / readout warps (16) =====================
+    const int we = warp - 2;                 // 0..15
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    // warps 2..9: warp%4 = {2,3,0,1,2,3,0,1}; the first four (we 0..3) take columns 0..127, the others 128..255
-    const int half = we >> 2;
+    const int cq = we >> 2;                  // column quarter: 64 columns of the residual layers, 32 of the last
     const int row = q * 32 + lane;
     const uint32_t xs_a = tc::smem_u32(xs);
+    const uint32_t rs_a = tc::smem_u32(rs);
     const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_corr = t_main + 256u;
     float* Z = reinterpret_cast<float*>(xs);
@@ -1093,12 +1093,12 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t a0 = tile * 128;
       const int rows = (int)min((int64_t)128, p.n_atoms - a0);
-      // ---- stage the node tile: warp `we` loads rows we, we+8, ... (1 KB coalesced per row),
+      // ---- stage the node tile: warp `we` loads rows we, we+16, ... (1 KB coalesced per row),
       //      lane = 8 consecutive features = one 16-byte piece of the hi tile and one of the lo tile
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's readout has finished with Z
+      asm volatile("bar.sync 1, 512;" ::: "memory");     // previous tile's readout has finished with Z
 #pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int r = we + i * 8;
+      for (int i = 0; i < 8; ++i) {
+        const int r = we + i * 16;
         float x[8];
         if (r < rows) {
           const float* src = p.nodes + (a0 + r) * 256 + lane * 8;
@@ -1136,20 +1136,20 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(x_full);
 
-      // ---- residual layers
+      // ---- residual layers: thread = (row, 64 columns = K-chunks 2cq, 2cq+1 of the next layer's operand)
       for (int l = 0; l + 1 < nl; ++l) {
         tc::mbar_wait(d_full, pd);
         pd ^= 1;
         tc::tc_fence_after();
-        const float* bl = bias_s + l * 256 + half * 128;
-        const float s_in = rs[l * 128 + row];              // 2^-s of this layer's input
-        const float s_nx = rs[(l + 1) * 128 + row];        // 2^-s' of the next layer's input
+        const uint32_t bl_a = tc::smem_u32(bias_s + l * 256 + cq * 64);
+        const float s_in = tc::lds32f(rs_a + (uint32_t)(l * 128 + row) * 4u);        // 2^-s of this layer's input
+        const float s_nx = tc::lds32f(rs_a + (uint32_t)((l + 1) * 128 + row) * 4u);  // 2^-s' of the next layer's input
         const float s_old = __fdiv_rn(1.0f, s_in);         // exact: s_in is a power of two
         const float s_out = p.corr * s_old;                // accumulator -> true scale, with the RZ compensation
 #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 0; cc < 4; ++cc) {
           float v[16];
-          const int col = half * 128 + cc * 16;
+          const int col = cq * 64 + cc * 16;
           tc::tmem_ld16_combined(t_main + col, t_corr + col, v);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -1158,6 +1158,8 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
             uint4 ohi, olo;
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(ohi.x), "=r"(ohi.y), "=r"(ohi.z), "=r"(ohi.w) : "r"(off));
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(olo.x), "=r"(olo.y), "=r"(olo.z), "=r"(olo.w) : "r"(off + 8192u));
+            const float4 b0 = tc::lds128(bl_a + (cc * 16 + hh * 8) * 4), b1 = tc::lds128(bl_a + (cc * 16 + hh * 8) * 4 + 16);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             const uint32_t oh[4] = {ohi.x, ohi.y, ohi.z, ohi.w}, ol[4] = {olo.x, olo.y, olo.z, olo.w};
             float x[8];
 #pragma unroll
@@ -1166,8 +1168,8 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
               const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ol[i]));
               const float old0 = fmaf(fl.x, tc::LO_UNSCALE, fh.x) * s_old;
               const float old1 = fmaf(fl.y, tc::LO_UNSCALE, fh.y) * s_old;
-              x[2 * i] = (apply_act(fmaf(v[hh * 8 + 2 * i], s_out, bl[cc * 16 + hh * 8 + 2 * i]), p.act) + old0) * s_nx;
-              x[2 * i + 1] = (apply_act(fmaf(v[hh * 8 + 2 * i + 1], s_out, bl[cc * 16 + hh * 8 + 2 * i + 1]), p.act) + old1) * s_nx;
+              x[2 * i] = (apply_act(fmaf(v[hh * 8 + 2 * i], s_out, bb[2 * i]), p.act) + old0) * s_nx;
+              x[2 * i + 1] = (apply_act(fmaf(v[hh * 8 + 2 * i + 1], s_out, bb[2 * i + 1]), p.act) + old1) * s_nx;
             }
             uint4 hi, lo;
             tc::split8_f16(x, hi, lo);
@@ -1180,57 +1182,58 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(x_full);
       }
-      // ---- last layer: Z = act(D + b), 128 columns; each (row, half) thread takes 64 of them
+      // ---- last layer: Z = act(D + b), 128 columns; each (row, quarter) thread takes 32 of them
       {
         const int l = nl - 1;
         tc::mbar_wait(d_full, pd);
         pd ^= 1;
         tc::tc_fence_after();
-        const float s_out = p.corr * __fdiv_rn(1.0f, rs[l * 128 + row]);
-        const float* bl = bias_s + l * 256 + half * 64;
-        float* zr = Z + row * FTC_LDZ + half * 64;
+        const float s_out = p.corr * __fdiv_rn(1.0f, tc::lds32f(rs_a + (uint32_t)(l * 128 + row) * 4u));
+        const uint32_t bl_a = tc::smem_u32(bias_s + l * 256 + cq * 32);
+        float* zr = Z + row * FTC_LDZ + cq * 32;
         // all MMAs that read X have completed (d_full); every warp must be past its own X reads too
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
           float v[16];
-          const int col = half * 64 + cc * 16;
+          const int col = cq * 32 + cc * 16;
           tc::tmem_ld16_combined(t_main + col, t_corr + col, v);
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
+            const float4 b4 = tc::lds128(bl_a + (cc * 16 + i) * 4);
             float4 o;
-            o.x = apply_act(fmaf(v[i + 0], s_out, bl[cc * 16 + i + 0]), p.act);
-            o.y = apply_act(fmaf(v[i + 1], s_out, bl[cc * 16 + i + 1]), p.act);
-            o.z = apply_act(fmaf(v[i + 2], s_out, bl[cc * 16 + i + 2]), p.act);
-            o.w = apply_act(fmaf(v[i + 3], s_out, bl[cc * 16 + i + 3]), p.act);
+            o.x = apply_act(fmaf(v[i + 0], s_out, b4.x), p.act);
+            o.y = apply_act(fmaf(v[i + 1], s_out, b4.y), p.act);
+            o.z = apply_act(fmaf(v[i + 2], s_out, b4.z), p.act);
+            o.w = apply_act(fmaf(v[i + 3], s_out, b4.w), p.act);
             *reinterpret_cast<float4*>(zr + cc * 16 + i) = o;
           }
         }
         tc::tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
       }
       if (p.fc_nodes != nullptr) {
-        for (int i = tid - 64; i < rows * 128; i += 256) {
+        for (int i = tid - 64; i < rows * 128; i += 512) {
           const int r = i >> 7, k = i & 127;
           p.fc_nodes[(a0 + r) * 128 + k] = Z[r * FTC_LDZ + k];
         }
       }
       // ---- readout: peaks = sum_c (z . Wo[:,c] + bo[c]) * a[c] * std[c] + a[c] * avg[c]; warp per atom,
-      //      skipping classes with a[c] == 0 (exact for finite activations).  The warp's 16 atom rows are
+      //      skipping classes with a[c] == 0 (exact for finite activations).  The warp's 8 atom rows are
       //      fetched up front (lane = class, all loads in flight together); classes beyond 32 take the slow loop.
       {
-        float av[16];
+        float av[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = we * 16 + i;
+        for (int i = 0; i < 8; ++i) {
+          const int r = we * 8 + i;
           av[i] = (r < rows && lane < p.C) ? __ldg(p.atoms + (a0 + r) * p.C + lane) : 0.0f;
         }
         const float std_l = lane < p.C ? __ldg(p.peak_std + lane) : 0.0f;
         const float avg_l = lane < p.C ? __ldg(p.peak_avg + lane) : 0.0f;
         const float bo_l = lane < p.C ? __ldg(p.bo + lane) : 0.0f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int r = we * 16 + i;
+        for (int i = 0; i < 8; ++i) {
+          const int r = we * 8 + i;
           if (r >= rows) continue;               // warp-uniform
           const float* zr = Z + r * FTC_LDZ;
           const float4 z4 = *reinterpret_cast<const float4*>(zr + lane * 4);   // this lane's 4 features
