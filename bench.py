@@ -36,6 +36,18 @@ K_NEIGH = 16
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+def mp_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one MP-layer launch from the committed ncu capture
+    (profiles/r01_mp_traffic.json; same workload).  None if no capture is on record."""
+    path = os.path.join(ROOT, "profiles", "r01_mp_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -81,7 +93,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -322,7 +334,9 @@ def run_ours(args):
         roofline = {
             "kernel": "mp_layer (" + h.compute_path + ")", "bound": "tensor",
             "achieved": mp_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": mp_tflops / peaks["bf16_tflops"], "traffic": None,
+            "frac": mp_tflops / peaks["bf16_tflops"], "traffic": mp_traffic_bytes(),
+            "traffic_note": "ncu dram bytes of one MP-layer launch (profiles/r01_final_ncu_summary.md); algorithmic "
+                            "bytes of the launch = atoms_per_gpu * 2308 + 786432",
             "peak_source": peaks["_source"] + " bf16 dense (MEASURED_PEAKS.json); the path needs fp32-accurate "
                            "products (FFMA or 3xTF32), so its reachable ceiling is far below the bf16 peak",
             "launch_ms": kern["mp_layer"], "share_of_step": 4 * kern["mp_layer"] / step_kernel_ms,
@@ -358,7 +372,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only (ncu)")
