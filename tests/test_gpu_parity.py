@@ -307,3 +307,64 @@ def test_tcgen05_selftest_gemm(model):
     assert f1 < 5e-3, "kind::f16 GEMM structurally wrong (layout/descriptor)"
     assert f3 < 1e-6, "fp16 scaled split does not reach fp32-level accuracy"
     assert f1 > 20 * f3
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties (the fp64 oracle is too slow for every run)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def config2_batch():
+    """configs[1]: 64 synthetic protein graphs, ~164 k atoms, K = 16 (the bench workload)."""
+    from nmrgnn_b200 import workloads
+    return workloads.protein_batch(64, first_seed=0)
+
+
+def test_config2_full_size_properties(model, config2_batch):
+    from nmrgnn_b200.workloads import take_graphs
+    atoms, nlist, edges, inv, offs = config2_batch
+    n = atoms.shape[0]
+    assert n > 100000
+    assert model.handle.compute_path.startswith("tcgen05")
+    y_tc = model((atoms, nlist, edges, inv))                       # default policy: tensor cores at this size
+    assert y_tc.shape == (n,) and np.all(np.isfinite(y_tc))
+    # (a) idempotence / determinism: the same call gives the same bits (also through the chunked upload path)
+    assert np.array_equal(model((atoms, nlist, edges, inv)), y_tc)
+    # (b) tensor-core path against the exact-FP32 kernels on all 164 k atoms
+    model.handle.set_option("force_ffma", 1)
+    try:
+        y_ff = model((atoms, nlist, edges, inv))
+    finally:
+        model.handle.set_option("force_ffma", 0)
+    tol = 1e-4 * np.abs(y_ff) + 1e-4
+    err = np.abs(y_tc - y_ff) / tol
+    assert np.mean(err <= 1.0) > 0.9995, float(np.mean(err <= 1.0))
+    assert np.quantile(err, 0.999) < 0.5
+    assert np.array_equal(y_tc == 0, y_ff == 0)
+    # (c) graphs are independent: three graphs evaluated alone (exact-FP32 route below 4096 atoms) agree with
+    #     their slice of the batched tensor-core result within the tolerance
+    for gidx in (0, 31, 63):
+        sub = take_graphs(config2_batch, np.array([gidx]))
+        yi = model(sub[:4])
+        a, b = int(offs[gidx]), int(offs[gidx + 1])
+        e = np.abs(y_tc[a:b] - yi) / (1e-4 * np.abs(yi) + 1e-4)
+        assert np.mean(e <= 1.0) > 0.999
+    # (d) sharding plan + reassembly reproduce the single-call result bit for bit (world_size 1 code path)
+    from nmrgnn_b200.sharding import ShardedModel
+    assert np.array_equal(ShardedModel(model)(config2_batch), y_tc)
+
+
+def test_config3_small_molecules_full_size(model):
+    """configs[2]: 1024 small molecules, K = 8 (~41 k atoms): both paths run and agree on well-conditioned peaks."""
+    from nmrgnn_b200 import workloads
+    atoms, nlist, edges, inv, offs = workloads.small_molecule_batch(1024, first_seed=0)
+    assert nlist.shape[1] == 8
+    y_tc = model((atoms, nlist, edges, inv))
+    model.handle.set_option("force_ffma", 1)
+    try:
+        y_ff = model((atoms, nlist, edges, inv))
+    finally:
+        model.handle.set_option("force_ffma", 0)
+    assert np.all(np.isfinite(y_tc)) and np.array_equal(y_tc == 0, y_ff == 0)
+    err = np.abs(y_tc - y_ff) / (1e-4 * np.abs(y_ff) + 1e-4)
+    assert np.mean(err <= 1.0) > 0.985          # random molecules: many ill-conditioned near-zero C/N peaks
+    assert np.median(err) < 0.05
