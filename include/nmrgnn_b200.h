@@ -153,8 +153,8 @@ int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap);
 
 /* Runtime options (value semantics per name):
  *   "tc_compensate" = 0: switch the compensation above off (diagnostics only; default 1);
- *   "tc_min_atoms" = n: calls with fewer than n atoms run on the exact-FP32 kernels (default 4096: below
- *                     one tile per SM both paths take one wave; 0 = always use tensor cores);
+ *   "tc_min_atoms" = n: calls with fewer than n atoms run on the exact-FP32 kernels (default 1024: a few
+ *                     128-row tiles, latency-bound on either path; 0 = always use tensor cores);
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "profile"    = 1: nmrgnn_forward records CUDA events (on the launching stream) around its
  *                     stages; read them with nmrgnn_stage_times. */

@@ -81,7 +81,7 @@ struct nmrgnn_handle {
   float fc_rz = 1.0f;
   bool compensate = true;
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
-  int64_t tc_min_atoms = 4096;          // calls smaller than this run on the exact-FP32 kernels (one wave either way)
+  int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
 };
 
 namespace {
@@ -412,8 +412,9 @@ bool mp_tc_usable(const nmrgnn_handle* h, int K) {
   return h->tc_ok && h->mp_tc_ok && !h->force_ffma && K >= 1 && K <= MTC_KMAX;
 }
 
-// Path policy of a whole call: the tensor-core kernels pay off once there are tiles for every SM; below
-// `tc_min_atoms` the exact-FP32 kernels are as fast (one wave) and carry no split/accumulation error.
+// Path policy of a whole call: below `tc_min_atoms` (a handful of 128-row tiles: latency-bound either way,
+// 1-2 ms) the exact-FP32 kernels are used and carry no split/accumulation error; a 2 482-atom protein already
+// runs 1.9x faster on the tensor-core kernels (tools/bench_md_stream.py).
 struct PathScope {
   nmrgnn_handle* h;
   bool saved;
