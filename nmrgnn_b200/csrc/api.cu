@@ -296,6 +296,24 @@ int grid_for(const nmrgnn_handle* h, int64_t tiles, int per_sm) {
   return (int)(tiles < g ? (tiles < 1 ? 1 : tiles) : g);
 }
 
+// the tensor-core kernels are instantiated per activation (common.cuh act_t)
+#define ACT_DISPATCH(act, kernel, grid, threads, smem, stream, args)                         \
+  do {                                                                                       \
+    switch (act) {                                                                           \
+      case ACT_SOFTPLUS: kernel<ACT_SOFTPLUS><<<grid, threads, smem, stream>>>(args); break; \
+      case ACT_RELU: kernel<ACT_RELU><<<grid, threads, smem, stream>>>(args); break;         \
+      case ACT_TANH: kernel<ACT_TANH><<<grid, threads, smem, stream>>>(args); break;         \
+      default: kernel<ACT_LINEAR><<<grid, threads, smem, stream>>>(args); break;             \
+    }                                                                                        \
+  } while (0)
+#define ACT_SET_SMEM(kernel, bytes)                                                                                  \
+  do {                                                                                                               \
+    CUDA_RC(cudaFuncSetAttribute(kernel<ACT_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
+    CUDA_RC(cudaFuncSetAttribute(kernel<ACT_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));  \
+    CUDA_RC(cudaFuncSetAttribute(kernel<ACT_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+    CUDA_RC(cudaFuncSetAttribute(kernel<ACT_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+  } while (0)
+
 // ------------------------------------------------------------------ launches
 int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
                 const int32_t* nlist, int64_t n_atoms, float4* rec = nullptr) {
@@ -325,7 +343,7 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     t.n_atoms = n_atoms;
     t.err_flag = h->err_flag;
     const int64_t tiles = (n_edges + 127) / 128;
-    edge_mlp_tc_kernel<<<grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s>>>(t);
+    ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
     h->launches++;
     return NMRGNN_OK;
   }
@@ -460,7 +478,7 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.raw = raw;
   a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
-  mp_layer_tc_kernel<<<grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s>>>(a);
+  ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   h->launches++;
   return NMRGNN_OK;
 }
@@ -491,7 +509,7 @@ int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float*
     t.peak_std = h->peak_std;
     t.peak_avg = h->peak_avg;
     const int64_t tiles = (n + 127) / 128;
-    fc_readout_tc_kernel<<<grid_for(h, tiles, 1), FTC_THREADS, FTC_SMEM, s>>>(t);
+    ACT_DISPATCH(t.act, fc_readout_tc_kernel, grid_for(h, tiles, 1), FTC_THREADS, FTC_SMEM, s, t);
     h->launches++;
     return NMRGNN_OK;
   }
@@ -808,7 +826,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     }
     TRY_RC(upload_bytes(h, img.data(), img.size(), &h->edge_f_img));
     TRY_RC(upload(h, bias.data(), bias.size(), &h->edge_bias));
-    CUDA_RC(cudaFuncSetAttribute(edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ETC_SMEM));
+    ACT_SET_SMEM(edge_mlp_tc_kernel, ETC_SMEM);
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STH_SMEM));
   }
@@ -833,7 +851,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
           F * E, F, F, img);
       TRY_RC(upload_bytes(h, img.data(), img.size(), &h->mp_img[l]));
     }
-    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MTC_SMEM));
+    ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
     h->mp_corr.assign(dims->n_mp, 1.0f);
     TRY_RC(calibrate_mp(h));
     h->launches = 0;
@@ -880,7 +898,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(upload_bytes(h, all.data(), all.size(), &h->fc_img));
     TRY_RC(upload(h, bias.data(), bias.size(), &h->fc_bias));
     h->fc_rz = 1.0f + 0.17f * (float)(F / 16 + 1) / 16777216.0f;
-    CUDA_RC(cudaFuncSetAttribute(fc_readout_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FTC_SMEM));
+    ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
   }
   h->path = "ffma";
   if (h->tc_ok) {

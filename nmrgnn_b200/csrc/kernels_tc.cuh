@@ -235,6 +235,7 @@ static_assert(true, "");
 constexpr size_t ETC_SMEM = 1024 + 2 * ETC_X_BYTES + ETC_RING * 16384 + ETC_CHUNKS * 2048 +
                             (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
 
+template <int ACT>
 __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
               float x[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                x[i] = apply_act(fmaf(v[hh * 8 + i], s_out, bb[i]), p.act) * s_in;
+                x[i] = act_t<ACT>(fmaf(v[hh * 8 + i], s_out, bb[i])) * s_in;
               uint4 hi, lo;
               tc::split8_f16(x, hi, lo);
               const uint32_t off = xg + tc::sw64_chunk_offset(row, cc * 2 + hh);
@@ -557,6 +558,7 @@ constexpr int MTC_KMAX = 16;
 constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * 32768 + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 static_assert(MTC_SMEM <= 227 * 1024, "MP tensor-core kernel exceeds the 227 KB shared-memory limit");
 
+template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~uintptr_t(511));
@@ -761,10 +763,10 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
           if (p.raw) {
             o = x[k];
           } else {
-            o.x = apply_act(x[k].x, p.act) + res[k].x;
-            o.y = apply_act(x[k].y, p.act) + res[k].y;
-            o.z = apply_act(x[k].z, p.act) + res[k].z;
-            o.w = apply_act(x[k].w, p.act) + res[k].w;
+            o.x = act_t<ACT>(x[k].x) + res[k].x;
+            o.y = act_t<ACT>(x[k].y) + res[k].y;
+            o.z = act_t<ACT>(x[k].z) + res[k].z;
+            o.w = act_t<ACT>(x[k].w) + res[k].w;
           }
           hm[k] = fmaxf(hm[k], fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
           if (grow + k < rows) *reinterpret_cast<float4*>(hout + k * 256 + cc * 32) = o;
@@ -995,6 +997,7 @@ constexpr size_t FTC_SMEM = 1024 + FTC_X_BYTES + FTC_RING * 16384 + MAX_DENSE * 
 static_assert(FTC_SMEM <= 227 * 1024, "node-MLP tensor-core kernel exceeds the 227 KB shared-memory limit");
 static_assert(128 * FTC_LDZ * 4 <= FTC_X_BYTES, "Z overlays the X operand");
 
+template <int ACT>
 __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcTcArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1168,8 +1171,8 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
               const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&ol[i]));
               const float old0 = fmaf(fl.x, tc::LO_UNSCALE, fh.x) * s_old;
               const float old1 = fmaf(fl.y, tc::LO_UNSCALE, fh.y) * s_old;
-              x[2 * i] = (apply_act(fmaf(v[hh * 8 + 2 * i], s_out, bb[2 * i]), p.act) + old0) * s_nx;
-              x[2 * i + 1] = (apply_act(fmaf(v[hh * 8 + 2 * i + 1], s_out, bb[2 * i + 1]), p.act) + old1) * s_nx;
+              x[2 * i] = (act_t<ACT>(fmaf(v[hh * 8 + 2 * i], s_out, bb[2 * i])) + old0) * s_nx;
+              x[2 * i + 1] = (act_t<ACT>(fmaf(v[hh * 8 + 2 * i + 1], s_out, bb[2 * i + 1])) + old1) * s_nx;
             }
             uint4 hi, lo;
             tc::split8_f16(x, hi, lo);
@@ -1202,10 +1205,10 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = tc::lds128(bl_a + (cc * 16 + i) * 4);
             float4 o;
-            o.x = apply_act(fmaf(v[i + 0], s_out, b4.x), p.act);
-            o.y = apply_act(fmaf(v[i + 1], s_out, b4.y), p.act);
-            o.z = apply_act(fmaf(v[i + 2], s_out, b4.z), p.act);
-            o.w = apply_act(fmaf(v[i + 3], s_out, b4.w), p.act);
+            o.x = act_t<ACT>(fmaf(v[i + 0], s_out, b4.x));
+            o.y = act_t<ACT>(fmaf(v[i + 1], s_out, b4.y));
+            o.z = act_t<ACT>(fmaf(v[i + 2], s_out, b4.z));
+            o.w = act_t<ACT>(fmaf(v[i + 3], s_out, b4.w));
             *reinterpret_cast<float4*>(zr + cc * 16 + i) = o;
           }
         }
