@@ -342,6 +342,7 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     t.nlist = nlist;
     t.n_atoms = n_atoms;
     t.err_flag = h->err_flag;
+    t.dbg = h->mp_dbg;
     const int64_t tiles = (n_edges + 127) / 128;
     ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
     h->launches++;

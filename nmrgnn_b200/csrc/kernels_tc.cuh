@@ -225,6 +225,7 @@ struct EdgeTcArgs {
   const int32_t* nlist;      // optional [n_edges]: validated against n_atoms (and packed into rec)
   int64_t n_atoms;
   int* err_flag;
+  long long* dbg;            // optional [gridDim][8] cycle counters (diagnostics)
 };
 
 constexpr int ETC_THREADS = 576;
@@ -304,13 +305,17 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
       const uint32_t idesc_f = tc::make_idesc_f16(128, 16);
       tc::mbar_wait(wf_full, 0);
       uint32_t it = 0, px[2] = {0, 0};
+      long long w_x = 0, w_w = 0, c0 = 0;
+      const long long k0 = clock64();
       for (int pair = 0; pair * 2 < n_my; ++pair)
         for (int l = 0; l <= n_hidden; ++l)
           for (int g = 0; g < 2; ++g) {
             if (pair * 2 + g >= n_my) continue;
             const bool fin = (l == n_hidden);
             const uint32_t d_main = tmem_base + (uint32_t)g * 256u, d_corr = d_main + 128u;
+            if (p.dbg) c0 = clock64();
             tc::mbar_wait(&x_full[g], px[g]);
+            if (p.dbg) w_x += clock64() - c0;
             px[g] ^= 1;
             tc::tc_fence_after();
             for (int c = 0; c < ETC_CHUNKS; ++c) {
@@ -318,7 +323,9 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
               uint32_t slot = 0;
               if (!fin) {
                 slot = it % ETC_RING;
+                if (p.dbg) c0 = clock64();
                 tc::mbar_wait(&w_full[slot], (it / ETC_RING) & 1);
+                if (p.dbg) w_w += clock64() - c0;
                 tc::tc_fence_after();
                 bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
                 bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
@@ -344,6 +351,12 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
             }
             tc::umma_commit(&d_full[g]);
           }
+      if (p.dbg) {
+        long long* o = p.dbg + (size_t)blockIdx.x * 8;
+        o[0] = clock64() - k0;   // MMA thread total
+        o[1] = w_x;              //   waiting for the epilogue warps (x_full)
+        o[2] = w_w;              //   waiting for W (w_full)
+      }
     }
   } else {
     // ===================== epilogue warps: thread = (edge row, 32 features = one K-chunk) =====================
@@ -411,7 +424,9 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
   #pragma unroll
       for (int g = 0; g < 2; ++g) {
         if (g >= n_in_pair) continue;
+          const long long q0 = p.dbg ? clock64() : 0;
           tc::mbar_wait(&d_full[g], pd[g]);
+          if (p.dbg && warp == 2 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 3), (unsigned long long)(clock64() - q0));
           pd[g] ^= 1;
           tc::tc_fence_after();
           const uint32_t t_main = t_lane + (uint32_t)g * 256u + col0, t_corr = t_main + 128u;
