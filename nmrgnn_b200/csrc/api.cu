@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels_ffma.cuh"
+#include "kernels_generic.cuh"
 #include "kernels_tc.cuh"
 #include "knn.cuh"
 
@@ -46,6 +47,8 @@ struct nmrgnn_handle {
   std::vector<const float*> edge_W, edge_b, fc_W, fc_b;
   const float* embed = nullptr;
   std::vector<const float*> mp_Wp;  // packed for the FFMA kernel
+  std::vector<const float*> mp_W;   // original [F,F,E] layout (generic-geometry kernels)
+  DevBuf genA, genB;                // generic-geometry activations
   const float *out_W = nullptr, *out_b = nullptr, *peak_std = nullptr, *peak_avg = nullptr;
   const float* centers = nullptr;
   float gap = 0.f;
@@ -315,10 +318,41 @@ int grid_for(const nmrgnn_handle* h, int64_t tiles, int per_sm) {
   } while (0)
 
 // ------------------------------------------------------------------ launches
+// generic-geometry route of the edge block: RBF tensor materialised, one dense kernel per layer
+int launch_edge_generic(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
+                        const int32_t* nlist, int64_t n_atoms) {
+  const int H = h->d.edge_hidden, E = h->d.edge_features, L = h->d.n_edge_fc;
+  int rc;
+  if (nlist != nullptr) {
+    gen_index_check_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, s>>>(nlist, n_edges, n_atoms, h->err_flag);
+    h->launches++;
+  }
+  // process in slabs so that the [edges, H] activations stay below ~1 GB each
+  const int64_t slab = std::max<int64_t>(1, ((int64_t)1 << 28) / std::max(H, 1));
+  if ((rc = ensure(h, h->genA, (size_t)std::min(slab, n_edges) * H * sizeof(float)))) return rc;
+  if ((rc = ensure(h, h->genB, (size_t)std::min(slab, n_edges) * H * sizeof(float)))) return rc;
+  for (int64_t e0 = 0; e0 < n_edges; e0 += slab) {
+    const int64_t ne = std::min(slab, n_edges - e0);
+    float* a = (float*)h->genA.p;
+    float* b = (float*)h->genB.p;
+    gen_rbf_kernel<<<(unsigned)((ne * H + 255) / 256), 256, 0, s>>>(edges + e0, h->centers, h->gap, a, ne, H);
+    h->launches++;
+    for (int l = 0; l < L; ++l) {
+      const bool last = l == L - 1;
+      gen_dense_kernel<<<(unsigned)ne, 256, 0, s>>>(a, h->edge_W[l], h->edge_b[l], nullptr, last ? edges + e0 : nullptr,
+                                                    last ? out + e0 * E : b, ne, H, last ? E : H,
+                                                    last ? ACT_LINEAR : h->d.fc_activation);
+      h->launches++;
+      std::swap(a, b);
+    }
+  }
+  return NMRGNN_OK;
+}
+
 int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
                 const int32_t* nlist, int64_t n_atoms, float4* rec = nullptr) {
   if (n_edges == 0) return NMRGNN_OK;
-  if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  if (!h->fast_path) return launch_edge_generic(h, s, edges, n_edges, out, nlist, n_atoms);
   if (h->tc_ok && !h->force_ffma) {
     EdgeTcArgs t{};
     t.edges = edges;
@@ -397,7 +431,15 @@ int launch_embed(nmrgnn_handle* h, cudaStream_t s, const float* atoms, int64_t n
 int launch_mp(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in, const int32_t* nlist,
               const float* efeat, const float* invdeg, int64_t n, int K, float* h_out, int raw = 0) {
   if (n == 0) return NMRGNN_OK;
-  if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  if (!h->fast_path) {
+    const int F = h->d.atom_features, E = h->d.edge_features;
+    if ((size_t)F * E * sizeof(float) > 200 * 1024) return fail(h, NMRGNN_ERR_BAD_DIMS, "atom_features * edge_features too large");
+    CUDA_TRY(h, cudaFuncSetAttribute(gen_mp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(F * E * sizeof(float))));
+    gen_mp_kernel<<<(unsigned)n, 256, F * E * sizeof(float), s>>>(h_in, nlist, efeat, invdeg, h->mp_W[layer], h_out, n, K, F, E,
+                                                                h->d.mp_activation);
+    h->launches++;
+    return NMRGNN_OK;
+  }
   MpArgs a{};
   a.h_in = h_in;
   a.h_out = h_out;
@@ -487,7 +529,28 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
 int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float* atoms, int64_t n, float* peaks,
               float* fc_nodes) {
   if (n == 0) return NMRGNN_OK;
-  if (!h->fast_path) return fail(h, NMRGNN_ERR_BAD_DIMS, "geometry not supported by the compiled kernels");
+  if (!h->fast_path) {
+    const int F = h->d.atom_features, F2 = F / 2, C = h->d.num_elem, L = h->d.n_fc;
+    int rc;
+    if ((rc = ensure(h, h->genA, (size_t)n * F * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->genB, (size_t)n * F * sizeof(float)))) return rc;
+    const float* x = nodes;
+    float* a = (float*)h->genA.p;
+    float* b = (float*)h->genB.p;
+    for (int l = 0; l < L; ++l) {
+      const bool last = l == L - 1;
+      float* y = (last && fc_nodes != nullptr) ? fc_nodes : a;
+      gen_dense_kernel<<<(unsigned)n, 256, 0, s>>>(x, h->fc_W[l], h->fc_b[l], last ? nullptr : x, nullptr, y, n, F,
+                                                   last ? F2 : F, h->d.fc_activation);
+      h->launches++;
+      x = y;
+      std::swap(a, b);
+    }
+    gen_readout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, atoms, h->out_W, h->out_b, h->peak_std, h->peak_avg,
+                                                                  peaks, n, F2, C);
+    h->launches++;
+    return NMRGNN_OK;
+  }
   if (h->fc_tc_ok && !h->force_ffma) {
     FcTcArgs t{};
     t.nodes = nodes;
@@ -666,7 +729,7 @@ void nmrgnn_destroy(nmrgnn_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (float* p : h->owned) cudaFree(p);
   for (DevBuf* b : {&h->atoms, &h->nlist, &h->edges, &h->invdeg, &h->efeat, &h->hA, &h->hB, &h->peaks, &h->tmp_in,
-                    &h->tmp_out, &h->pos, &h->offs, &h->rec, &h->hmaxA, &h->hmaxB})
+                    &h->tmp_out, &h->pos, &h->offs, &h->rec, &h->hmaxA, &h->hmaxB, &h->genA, &h->genB})
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->err_flag) cudaFree(h->err_flag);
@@ -766,6 +829,10 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
             for (int m = 0; m < F; ++m) packed[((size_t)lf * E + n) * F + m] = src[((size_t)lf * F + m) * E + n];
       }
       TRY_RC(upload(h, packed.data(), packed.size(), &h->mp_Wp[l]));
+      if (!(F == 256 && H == 128 && E >= 1 && E <= 4)) {
+        h->mp_W.resize(dims->n_mp);
+        TRY_RC(upload(h, src, (size_t)F * F * E, &h->mp_W[l]));
+      }
     }
   }
   h->fc_W.resize(dims->n_fc);
@@ -901,7 +968,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     h->fc_rz = 1.0f + 0.17f * (float)(F / 16 + 1) / 16777216.0f;
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
   }
-  h->path = "ffma";
+  h->path = h->fast_path ? "ffma" : "generic-fp32";
   if (h->tc_ok) {
     h->path = "tcgen05-fp16x3(edge";
     if (h->mp_tc_ok) h->path += ",mp";
