@@ -83,6 +83,7 @@ struct nmrgnn_handle {
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
   bool compensate = true;
+  bool edge_ts = false;                 // option "edge_ts": the TS-form edge kernel (activation operand in tensor memory)
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
 };
@@ -378,7 +379,8 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     t.err_flag = h->err_flag;
     t.dbg = h->mp_dbg;
     const int64_t tiles = (n_edges + 127) / 128;
-    ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
+    if (!h->edge_ts) ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
+    else ACT_DISPATCH(t.act, edge_mlp_ts_kernel, grid_for(h, tiles, 1), ETS_THREADS, ETS_SMEM, s, t);
     h->launches++;
     return NMRGNN_OK;
   }
@@ -895,8 +897,10 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(upload_bytes(h, img.data(), img.size(), &h->edge_f_img));
     TRY_RC(upload(h, bias.data(), bias.size(), &h->edge_bias));
     ACT_SET_SMEM(edge_mlp_tc_kernel, ETC_SMEM);
+    ACT_SET_SMEM(edge_mlp_ts_kernel, ETS_SMEM);
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STH_SMEM));
+    CUDA_RC(cudaFuncSetAttribute(tc_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STH_SMEM));
   }
   h->mp_tc_ok = h->tc_ok && E <= 3 && dims->n_mp >= 1;
   if (h->mp_tc_ok) {
@@ -1217,7 +1221,7 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
   int rc = begin_call(h, NMRGNN_MEM_HOST, nullptr, &s);
   if (rc) return rc;
   if (!A || !W || !D) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
-  if (mode < 0 || mode > 3) return fail(h, NMRGNN_ERR_BAD_DIMS, "mode must be 0..3");
+  if (mode < 0 || mode > 4) return fail(h, NMRGNN_ERR_BAD_DIMS, "mode must be 0..4");
   if (!h->tc_ok) return fail(h, NMRGNN_ERR_BAD_DIMS, "tensor-core path not available for this geometry");
   std::vector<uint8_t> img;
   if (mode <= 1) pack_sw64(W, ST_K, 128, 0, 128, 128, img);
@@ -1230,6 +1234,7 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
   CUDA_TRY(h, cudaMemcpyAsync(d_A, A, 128 * ST_K * sizeof(float), cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaStreamSynchronize(s));  // img is a local vector
   if (mode <= 1) tc_selftest_kernel<<<1, 192, ST_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
+  else if (mode == 4) tc_selftest_ts_kernel<<<1, 192, STH_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p);
   else tc_selftest_f16_kernel<<<1, 192, STH_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
   h->launches++;
   CUDA_TRY(h, cudaMemcpyAsync(D, h->tmp_out.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1290,6 +1295,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
                n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[5] / n, m[6] / n);
     }
     if (value == 0) h->mp_dbg = nullptr;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "edge_ts") == 0) {
+    h->edge_ts = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "tc_min_atoms") == 0) {
