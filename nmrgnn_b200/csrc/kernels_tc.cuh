@@ -650,8 +650,8 @@ __global__ void __launch_bounds__(ETS_THREADS, 1) edge_mlp_ts_kernel(const EdgeT
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && n_my > 0) {
-      const uint32_t idesc_h = tc::make_idesc_f16(128, 128);
-      const uint32_t idesc_f = tc::make_idesc_f16(128, 16);
+      const uint32_t idesc_h2 = tc::make_idesc_f16(128, 256), idesc_h = tc::make_idesc_f16(128, 128);
+      const uint32_t idesc_f2 = tc::make_idesc_f16(128, 32), idesc_f = tc::make_idesc_f16(128, 16);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + 128u;
       tc::mbar_wait(wf_full, 0);
       uint32_t it = 0, px[2] = {0, 0}, use = 0;
@@ -686,14 +686,13 @@ __global__ void __launch_bounds__(ETS_THREADS, 1) edge_mlp_ts_kernel(const EdgeT
                 bh = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048));
                 bl = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048 + 1024));
               }
-              const uint32_t idesc = fin ? idesc_f : idesc_h;
+              (void)bl;
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);
                 const uint32_t ah = xa + (uint32_t)(c * 2 + ks) * 8u, al = ah + 64u;
-                tc::umma_f16_ts(d_main, ah, bh + adv, idesc, (c | ks) != 0);
-                tc::umma_f16_ts(d_corr, al, bh + adv, idesc, (c | ks) != 0);
-                tc::umma_f16_ts(d_corr, ah, bl + adv, idesc, 1);
+                tc::umma_f16_ts(d_main, ah, bh + adv, fin ? idesc_f2 : idesc_h2, (c | ks) != 0);
+                tc::umma_f16_ts(fin ? d_main + 16u : d_corr, al, bh + adv, fin ? idesc_f : idesc_h, 1);
               }
               if (!fin) {
                 tc::umma_commit(&w_empty[slot]);
@@ -818,7 +817,7 @@ __global__ void __launch_bounds__(ETS_THREADS, 1) edge_mlp_ts_kernel(const EdgeT
         float va[8], vb[8];
         if (cq == 0) {
           tc::tmem_ld8(t_lane, va);
-          tc::tmem_ld8(t_lane + 128u, vb);
+          tc::tmem_ld8(t_lane + 16u, vb);
         }
         tc::tc_fence_before();
         __syncwarp();
