@@ -1419,7 +1419,9 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(128, 128);
+      // per 128-column half h: tensor-memory columns [256h, 256h+128) = main, [256h+128, 256h+256) = corr, so that
+      // x_hi * [w_hi | w_lo] -> [main | corr] is ONE N = 256 instruction (the slot holds the hi and lo tiles adjacently)
+      const uint32_t idesc = tc::make_idesc_f16(128, 128), idesc2 = tc::make_idesc_f16(128, 256);
       uint32_t it = 0, px = 0;
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int l = 0; l < nl; ++l) {
@@ -1435,14 +1437,12 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
               tc::mbar_wait(&w_full[slot], (it / FTC_RING) & 1);
               tc::tc_fence_after();
               const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
-              const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
-              const uint32_t d_main = tmem_base + (uint32_t)hf * 128u, d_corr = d_main + 256u;
+              const uint32_t d_main = tmem_base + (uint32_t)hf * 256u, d_corr = d_main + 128u;
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);
-                tc::umma_f16(d_main, ah + adv, bh + adv, idesc, (c | ks) != 0);
-                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, (c | ks) != 0);
-                tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+                tc::umma_f16(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, 1);
               }
               tc::umma_commit(&w_empty[slot]);
             }
@@ -1458,8 +1458,7 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
     const int row = q * 32 + lane;
     const uint32_t xs_a = tc::smem_u32(xs);
     const uint32_t rs_a = tc::smem_u32(rs);
-    const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t t_corr = t_main + 256u;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* Z = reinterpret_cast<float*>(xs);
     uint32_t pd = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -1522,7 +1521,8 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
         for (int cc = 0; cc < 4; ++cc) {
           float v[16];
           const int col = cq * 64 + cc * 16;
-          tc::tmem_ld16_combined(t_main + col, t_corr + col, v);
+          const uint32_t t_main = t_lane + (uint32_t)(col >> 7) * 256u + (uint32_t)(col & 127);
+          tc::tmem_ld16_combined(t_main, t_main + 128u, v);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             const int k0 = col + hh * 8;
@@ -1569,7 +1569,7 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
         for (int cc = 0; cc < 2; ++cc) {
           float v[16];
           const int col = cq * 32 + cc * 16;
-          tc::tmem_ld16_combined(t_main + col, t_corr + col, v);
+          tc::tmem_ld16_combined(t_lane + col, t_lane + 128u + col, v);
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const float4 b4 = tc::lds128(bl_a + (cc * 16 + i) * 4);
