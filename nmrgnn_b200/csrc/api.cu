@@ -350,8 +350,10 @@ int launch_edge_generic(nmrgnn_handle* h, cudaStream_t s, const float* edges, in
   return NMRGNN_OK;
 }
 
+bool rec_swizzled(int K) { return K == 8 || K == 16; }
+
 int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
-                const int32_t* nlist, int64_t n_atoms, float4* rec = nullptr) {
+                const int32_t* nlist, int64_t n_atoms, float4* rec = nullptr, int K = 0, int64_t e0 = 0) {
   if (n_edges == 0) return NMRGNN_OK;
   if (!h->fast_path) return launch_edge_generic(h, s, edges, n_edges, out, nlist, n_atoms);
   if (h->tc_ok && !h->force_ffma) {
@@ -378,6 +380,8 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     t.n_atoms = n_atoms;
     t.err_flag = h->err_flag;
     t.dbg = h->mp_dbg;
+    t.rec_k = (rec != nullptr && rec_swizzled(K)) ? K : 0;
+    t.rec_e0 = e0;
     const int64_t tiles = (n_edges + 127) / 128;
     if (!h->edge_ts) ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
     else ACT_DISPATCH(t.act, edge_mlp_ts_kernel, grid_for(h, tiles, 1), ETS_THREADS, ETS_SMEM, s, t);
@@ -495,10 +499,11 @@ int launch_absmax(nmrgnn_handle* h, cudaStream_t s, const float* nodes, int64_t 
 }
 
 int launch_pack_rec(nmrgnn_handle* h, cudaStream_t s, const int32_t* nlist, const float* efeat, float4* rec,
-                    int64_t n_edges, int64_t n_atoms) {
+                    int64_t n_edges, int64_t n_atoms, int K) {
   if (n_edges == 0) return NMRGNN_OK;
   pack_edge_records_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, s>>>(nlist, efeat, rec, n_edges,
-                                                                              h->d.edge_features, n_atoms, h->err_flag);
+                                                                              h->d.edge_features, n_atoms, h->err_flag,
+                                                                              rec_swizzled(K) ? K : 0);
   h->launches++;
   return NMRGNN_OK;
 }
@@ -521,6 +526,7 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.act = h->d.mp_activation;
   a.corr = (h->compensate && !raw) ? h->mp_corr[layer] : 1.0f;
   a.raw = raw;
+  a.swz = rec_swizzled(K) ? 1 : 0;
   a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
   ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
@@ -663,7 +669,7 @@ int calibrate_mp(nmrgnn_handle* h) {
   h->force_ffma = saved;
   if (rc) return rc;
   if ((rc = launch_pack_rec(h, s, (const int32_t*)h->nlist.p, (const float*)h->efeat.p, (float4*)h->rec.p,
-                            (int64_t)N * K, N)))
+                            (int64_t)N * K, N, K)))
     return rc;
   float* ha = (float*)h->hA.p;
   float* hb = (float*)h->hB.p;
@@ -1060,7 +1066,7 @@ int nmrgnn_mp_layer(nmrgnn_handle* h, int32_t layer, const float* nodes_in, cons
     if ((rc = ensure(h, h->rec, n_atoms * k * sizeof(float4)))) return rc;
     if ((rc = ensure(h, h->hmaxA, n_atoms * sizeof(float)))) return rc;
     if ((rc = ensure(h, h->hmaxB, n_atoms * sizeof(float)))) return rc;
-    if ((rc = launch_pack_rec(h, s, (const int32_t*)d_nl, (const float*)d_ef, (float4*)h->rec.p, n_atoms * k, n_atoms)))
+    if ((rc = launch_pack_rec(h, s, (const int32_t*)d_nl, (const float*)d_ef, (float4*)h->rec.p, n_atoms * k, n_atoms, k)))
       return rc;
     if ((rc = launch_absmax(h, s, (const float*)d_in, n_atoms, (float*)h->hmaxA.p))) return rc;
     if ((rc = launch_mp_tc(h, s, layer, (const float*)d_in, (const float*)h->hmaxA.p, (const float4*)h->rec.p,
@@ -1179,7 +1185,7 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
       const int64_t a0 = c * chunk_atoms, na = std::min<int64_t>(chunk_atoms, n_atoms - a0);
       if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[c], 0));
       if ((rc = launch_edge(h, s, (const float*)d_edges + a0 * k, na * k, nullptr, (const int32_t*)d_nl + a0 * k, n_atoms,
-                            rec + a0 * k)))
+                            rec + a0 * k, k, a0 * k)))
         return rc;
     }
     mark();

@@ -299,7 +299,20 @@ struct EdgeTcArgs {
   int64_t n_atoms;
   int* err_flag;
   long long* dbg;            // optional [gridDim][8] cycle counters (diagnostics)
+  int rec_k;                 // K (8 or 16) if the records are slot-swizzled for the MP kernel (rec_slot), else 0
+  int64_t rec_e0;            // edge index of this launch's first edge within the whole batch (chunked launches)
 };
+
+// Edge records of one atom are stored slot-swizzled: logical neighbour j of atom i sits in slot j ^ ((i & 3) << 1).
+// The MP producers process 4 consecutive atoms per warp and read the same logical slot of all four in one shared
+// memory instruction; with a 256-byte row stride those four 16-byte reads would hit the same banks (4-way conflict,
+// measured: 2/3 of the kernel's L1 wavefronts).  The swizzle spreads them over 4 bank groups while every atom still
+// accumulates its neighbours in logical order (bit-identical results, independent of the atom's position in a batch).
+__host__ __device__ __forceinline__ int64_t rec_slot(int64_t e, int K) {   // K = 8 or 16
+  const int sh = K == 16 ? 4 : 3;
+  const int64_t atom = e >> sh;
+  return e ^ (int64_t)((atom & 3) << 1);      // flips bits 1..2 of the slot index j = e & (K - 1)
+}
 
 constexpr int ETC_THREADS = 576;
 constexpr int ETC_RING = 4;
@@ -554,7 +567,10 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
               o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
             if (p.out != nullptr)
               for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
-            if (p.rec != nullptr) p.rec[e] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+            if (p.rec != nullptr) {
+              const int64_t er = p.rec_k ? rec_slot(p.rec_e0 + e, p.rec_k) - p.rec_e0 : e;
+              p.rec[er] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+            }
           }
         }
         tc::tc_fence_before();
@@ -833,7 +849,10 @@ __global__ void __launch_bounds__(ETS_THREADS, 1) edge_mlp_ts_kernel(const EdgeT
               o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
             if (p.out != nullptr)
               for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
-            if (p.rec != nullptr) p.rec[e] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+            if (p.rec != nullptr) {
+              const int64_t er = p.rec_k ? rec_slot(p.rec_e0 + e, p.rec_k) - p.rec_e0 : e;
+              p.rec[er] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+            }
           }
         }
       }
@@ -855,7 +874,8 @@ namespace nmr {
 // out-of-range indices are flagged and replaced by 0 (the call then fails with BAD_INDEX).
 __global__ void __launch_bounds__(256) pack_edge_records_kernel(const int32_t* __restrict__ nlist,
                                                                 const float* __restrict__ efeat, float4* __restrict__ rec,
-                                                                int64_t n_edges, int E, int64_t n_atoms, int* err_flag) {
+                                                                int64_t n_edges, int E, int64_t n_atoms, int* err_flag,
+                                                                int rec_k) {
   const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (e >= n_edges) return;
   int32_t idx = nlist[e];
@@ -867,7 +887,7 @@ __global__ void __launch_bounds__(256) pack_edge_records_kernel(const int32_t* _
   r.x = efeat[e * E];
   if (E > 1) r.y = efeat[e * E + 1];
   if (E > 2) r.z = efeat[e * E + 2];
-  rec[e] = r;
+  rec[rec_k ? rec_slot(e, rec_k) : e] = r;
 }
 
 // hmax[i] = max_l |h[i, l]|, F = 256: one warp per atom
@@ -916,6 +936,7 @@ struct MpTcArgs {
   int act;
   float corr;                // 1 + c: compensates the round-toward-zero accumulation of tcgen05
   int raw;                   // 1: h_out = inv_degree * D (no activation, no residual) -- calibration tap
+  int swz;                   // records are slot-swizzled (rec_slot; K = 8 or 16)
   long long* dbg;            // optional [gridDim][8] cycle counters (diagnostics): see tools/diag_mp_roles.py
 };
 
@@ -1187,12 +1208,13 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       // neighbour indices are fetched one half-step ahead of the row loads that use them (`nidx`), so the
       // address computation never waits for shared memory
       uint32_t nidx[8];
+      const uint32_t sw = p.swz ? (uint32_t)(rsub << 1) : 0u;   // row & 3 == rsub for every row this thread touches
       auto load_idx = [&](int row, int half, bool FULL) {
         const bool rv = row < rows;
-        const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u + 12u;
+        const uint32_t ra = rec_a + (uint32_t)(row * K) * 16u + 12u;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          uint32_t idx = tc::lds32(ra + u * 16);
+          uint32_t idx = tc::lds32(ra + (((uint32_t)(half * 8 + u)) ^ sw) * 16u);
           if (!FULL) idx = (rv && half * 8 + u < K) ? idx : 0u;
           nidx[u] = idx;
         }
@@ -1204,10 +1226,10 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       };
       auto consume = [&](const float4 (&hv)[8], int row, int half, float (&acc)[3][4], bool FULL) {
         const bool rv = row < rows;
-        const uint32_t ra = rec_a + (uint32_t)(row * K + half * 8) * 16u;
+        const uint32_t ra = rec_a + (uint32_t)(row * K) * 16u;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          float4 r = tc::lds128(ra + u * 16);
+          float4 r = tc::lds128(ra + (((uint32_t)(half * 8 + u)) ^ sw) * 16u);
           if (!FULL) {
             const bool ok = rv && half * 8 + u < K;
             r.x = ok ? r.x : 0.0f;
