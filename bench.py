@@ -131,9 +131,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_workload(rank: int, n_graphs: int):
+def make_workload(rank: int, n_graphs: int, world: int = 1, graphs_total: int = 0):
+    """Weak scaling (default): every rank generates its own `n_graphs` graphs (seeds rank*n .. rank*n+n-1).
+    Strong scaling (--graphs-total G, BASELINE config 4): the G graphs with seeds 0..G-1 are assigned to ranks by the
+    greedy atom-count balance of nmrgnn_b200.sharding.ShardPlan; a rank only generates the graphs it owns."""
     from nmrgnn_b200 import workloads
-    return workloads.protein_batch(n_graphs, first_seed=rank * n_graphs, neighbor_number=K_NEIGH)
+    if graphs_total <= 0:
+        return workloads.protein_batch(n_graphs, first_seed=rank * n_graphs, neighbor_number=K_NEIGH)
+    from nmrgnn_b200.graph import batch_graphs
+    from nmrgnn_b200.sharding import ShardPlan
+    sizes = np.array([workloads.protein_graph_size(s) for s in range(graphs_total)], np.int64)
+    plan = ShardPlan(np.concatenate([[0], np.cumsum(sizes)]), world)
+    graphs = workloads.protein_graphs([int(g) for g in plan.owned[rank]], neighbor_number=K_NEIGH)
+    return batch_graphs(graphs)
 
 
 def workload_config(n_gpus, **extra):
@@ -221,7 +231,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    batch = make_workload(rank, GRAPHS_PER_GPU)
+    batch = make_workload(rank, GRAPHS_PER_GPU, world, args.graphs_total)
     atoms, nlist, edges, inv, offs = batch
     n_atoms = int(atoms.shape[0])
     model = nmrgnn_b200.load_model(device=local_rank)
@@ -350,11 +360,15 @@ def run_ours(args):
         cpu = None if args.skip_cpu_baseline else cpu_baseline(batch)
         line = {
             "metric": "atoms/sec MP-GNN forward", "value": value, "unit": "atoms/s",
-            "graphs_per_s": world * GRAPHS_PER_GPU / (ms_step * 1e-3),
+            "graphs_per_s": (args.graphs_total if args.graphs_total > 0 else world * GRAPHS_PER_GPU) / (ms_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.graphs_total > 0 else "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": workload_config(world, atoms_per_gpu=n_atoms, total_atoms=total_atoms,
-                                      compute_path=h.compute_path),
+                                      compute_path=h.compute_path,
+                                      **({"workload": f"config[3]: batch of {args.graphs_total} synthetic protein graphs "
+                                                      f"sharded by graph over {world} GPU(s), all-gather of peaks",
+                                          "graphs_total": args.graphs_total} if args.graphs_total > 0 else {})),
             "clocks": clocks,
             "e2e": {"value": total_atoms / (e2e_ms * 1e-3), "unit": "atoms/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -376,6 +390,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only (ncu)")
+    ap.add_argument("--graphs-total", type=int, default=0,
+                    help="strong scaling: a fixed batch of this many graphs sharded over the ranks (BASELINE config 4 = 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
