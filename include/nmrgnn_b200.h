@@ -156,6 +156,10 @@ int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap);
  *   "tc_min_atoms" = n: calls with fewer than n atoms run on the exact-FP32 kernels (default 1024: a few
  *                     128-row tiles, latency-bound on either path; 0 = always use tensor cores);
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
+ *   "edge_ts" = 1: edge MLP with its activation operand in tensor memory (TS-form tcgen05.mma; bit-identical
+ *                  output, measured slower than the default SS form; kept for comparison);
+ *   "mp_role_counters" = 1 / 2 / 0: diagnostics -- arm per-CTA cycle counters of the warp roles of the next MP-layer
+ *                  or edge launch / print their means to stdout / disarm;
  *   "profile"    = 1: nmrgnn_forward records CUDA events (on the launching stream) around its
  *                     stages; read them with nmrgnn_stage_times. */
 int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value);
