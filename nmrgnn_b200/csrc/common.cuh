@@ -11,9 +11,13 @@ enum : int { ACT_LINEAR = 0, ACT_SOFTPLUS = 1, ACT_RELU = 2, ACT_TANH = 3 };
 // log(exp(x) + 1) with thresholds (tensorflow/core/kernels/softplus_op.h); both
 // forms carry an absolute error of ~eps/2 from rounding 1+t, so the MUFU-based
 // ex2/lg2 evaluation below (2 MUFU + 4 FP32 ops) stays inside that envelope.
+// (ex2.approx.ftz / lg2.approx directly: __expf() adds a compare and two predicated multiplies per call to keep
+//  results below 2^-126 denormal-exact, which log(1 + t) cannot see)
 __device__ __forceinline__ float softplus_f(float x) {
-  float t = __expf(-fabsf(x));
-  return fmaxf(x, 0.0f) + __logf(1.0f + t);
+  float t, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(x)));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
+  return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
