@@ -373,6 +373,7 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     t.Wfimg = h->edge_f_img;
     t.bias = h->edge_bias;
     t.bias_f = h->edge_b[h->d.n_edge_fc - 1];
+    t.Wf = h->edge_W[h->d.n_edge_fc - 1];
     t.n_hidden = h->d.n_edge_fc - 1;
     t.E = h->d.edge_features;
     t.act = h->d.fc_activation;
@@ -869,7 +870,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     CUDA_RC(cudaFuncSetAttribute(edge_mlp_ffma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)edge_smem_bytes<4>()));
   }
   // tensor-core path: fp16 scaled-split operands need every weight below the fp16 range
-  h->tc_ok = h->fast_path && E <= 8 && dims->n_edge_fc >= 2;
+  h->tc_ok = h->fast_path && E <= 4 && dims->n_edge_fc >= 2;
   if (h->tc_ok) {
     const int n_hidden = dims->n_edge_fc - 1;
     std::vector<uint8_t> img, all;

@@ -290,6 +290,7 @@ struct EdgeTcArgs {
   const uint8_t* Wfimg;      // final layer:   [4 chunks][hi 1024 | lo 1024]   (16 rows, rows >= E are zero)
   const float* bias;         // [n_hidden][128]
   const float* bias_f;       // [E]
+  const float* Wf;           // final layer, fp32 [128][E] (the SS kernel evaluates it on the CUDA cores)
   float in_scale[MAX_DENSE + 1];   // power of two applied to the INPUT of layer l (a-priori range bound)
   float out_scale[MAX_DENSE + 1];  // its inverse, applied to the accumulator of layer l
   int n_hidden;              // hidden (activated) layers, >= 1
@@ -319,7 +320,7 @@ constexpr int ETC_RING = 4;
 constexpr int ETC_CHUNKS = 4;          // 128 / 32
 constexpr int ETC_X_BYTES = ETC_CHUNKS * 16384;
 static_assert(true, "");
-constexpr size_t ETC_SMEM = 1024 + 2 * ETC_X_BYTES + ETC_RING * 16384 + ETC_CHUNKS * 2048 +
+constexpr size_t ETC_SMEM = 1024 + 2 * ETC_X_BYTES + ETC_RING * 16384 + 128 * 16 + 2 * 4 * 128 * 16 +
                             (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
 
 template <int ACT>
@@ -328,8 +329,9 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xs = smem;                                     // [2 slots][4 chunks][hi 8192 | lo 8192]
   uint8_t* ring = xs + 2 * ETC_X_BYTES;                   // [RING][hi 8192 | lo 8192]
-  uint8_t* wf = ring + ETC_RING * 16384;                  // [4][hi 1024 | lo 1024]
-  float* bias_s = reinterpret_cast<float*>(wf + ETC_CHUNKS * 2048);   // [n_hidden][128]
+  float4* wf4 = reinterpret_cast<float4*>(ring + ETC_RING * 16384);   // [128] final-layer weights {w[k][0..2], 0}
+  float4* part = wf4 + 128;                               // [2 slots][4 column quarters][128 rows] partial outputs
+  float* bias_s = reinterpret_cast<float*>(part + 2 * 4 * 128);        // [n_hidden][128]
   float* cen_s = bias_s + MAX_DENSE * 128;                // [128]
   float* bf_s = cen_s + 128;                              // [16]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bf_s + 16);
@@ -356,6 +358,9 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
   for (int i = tid; i < p.n_hidden * 128; i += ETC_THREADS) bias_s[i] = p.bias[i];
   for (int i = tid; i < 128; i += ETC_THREADS) cen_s[i] = p.centers[i];
   if (tid < 16) bf_s[tid] = tid < p.E ? p.bias_f[tid] : 0.0f;
+  for (int i = tid; i < 128; i += ETC_THREADS)
+    wf4[i] = make_float4(p.Wf[i * p.E], p.E > 1 ? p.Wf[i * p.E + 1] : 0.0f, p.E > 2 ? p.Wf[i * p.E + 2] : 0.0f,
+                         p.E > 3 ? p.Wf[i * p.E + 3] : 0.0f);
   if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
   tc::tc_fence_before();
   __syncthreads();
@@ -369,8 +374,6 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
   if (warp == 0) {
     // ===================== weight loader =====================
     if (lane == 0 && n_my > 0) {
-      tc::mbar_expect_tx(wf_full, ETC_CHUNKS * 2048);
-      tc::bulk_g2s(wf, p.Wfimg, ETC_CHUNKS * 2048, wf_full);
       uint32_t it = 0;
       for (int pair = 0; pair * 2 < n_my; ++pair)
         for (int l = 0; l < n_hidden; ++l)
@@ -390,53 +393,40 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
       // A tcgen05.mma costs >= ~105 cycles however small it is (tools/microbench/mma_rate.cu), so the two products
       // that share the A operand are issued as ONE instruction: the hi and lo weight tiles are adjacent in the
       // image (256 rows) and main / corr adjacent in tensor memory, i.e. x_hi * [w_hi | w_lo] -> [main | corr].
+      // For the same reason the last (128 -> E, E <= 3) layer is NOT a tensor-core layer: it would be 16
+      // near-empty instructions per tile; the epilogue warps evaluate it in exact FP32 (below).
       const uint32_t idesc_h2 = tc::make_idesc_f16(128, 256), idesc_h = tc::make_idesc_f16(128, 128);
-      const uint32_t idesc_f2 = tc::make_idesc_f16(128, 32), idesc_f = tc::make_idesc_f16(128, 16);
-      tc::mbar_wait(wf_full, 0);
       uint32_t it = 0, px[2] = {0, 0};
       long long w_x = 0, w_w = 0, c0 = 0;
       const long long k0 = clock64();
       for (int pair = 0; pair * 2 < n_my; ++pair)
-        for (int l = 0; l <= n_hidden; ++l)
+        for (int l = 0; l < n_hidden; ++l)
           for (int g = 0; g < 2; ++g) {
             if (pair * 2 + g >= n_my) continue;
-            const bool fin = (l == n_hidden);
             const uint32_t d_main = tmem_base + (uint32_t)g * 256u, d_corr = d_main + 128u;
             if (p.dbg) c0 = clock64();
             tc::mbar_wait(&x_full[g], px[g]);
             if (p.dbg) w_x += clock64() - c0;
             px[g] ^= 1;
             tc::tc_fence_after();
-            for (int c = 0; c < ETC_CHUNKS; ++c) {
-              uint64_t bh, bl;
-              uint32_t slot = 0;
-              if (!fin) {
-                slot = it % ETC_RING;
-                if (p.dbg) c0 = clock64();
-                tc::mbar_wait(&w_full[slot], (it / ETC_RING) & 1);
-                if (p.dbg) w_w += clock64() - c0;
-                tc::tc_fence_after();
-                bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
-                bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
-              } else {
-                bh = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048));
-                bl = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048 + 1024));
-              }
+            for (int c = 0; c < ETC_CHUNKS; ++c, ++it) {
+              const uint32_t slot = it % ETC_RING;
+              if (p.dbg) c0 = clock64();
+              tc::mbar_wait(&w_full[slot], (it / ETC_RING) & 1);
+              if (p.dbg) w_w += clock64() - c0;
+              tc::tc_fence_after();
+              const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
               const uint8_t* xc = xs + g * ETC_X_BYTES + c * 16384;
               const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(xc));
               const uint64_t al = tc::make_desc_sw64(tc::smem_u32(xc + 8192));
-              (void)bl;
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);
-                // hidden: [main | corr] (+)= x_hi * [w_hi | w_lo];  final: columns [0,16) main, [16,32) corr
-                tc::umma_f16(d_main, ah + adv, bh + adv, fin ? idesc_f2 : idesc_h2, (c | ks) != 0);
-                tc::umma_f16(fin ? d_main + 16u : d_corr, al + adv, bh + adv, fin ? idesc_f : idesc_h, 1);
+                // [main | corr] (+)= x_hi * [w_hi | w_lo], then corr += x_lo * w_hi
+                tc::umma_f16(d_main, ah + adv, bh + adv, idesc_h2, (c | ks) != 0);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc_h, 1);
               }
-              if (!fin) {
-                tc::umma_commit(&w_empty[slot]);
-                ++it;
-              }
+              tc::umma_commit(&w_empty[slot]);
             }
             tc::umma_commit(&d_full[g]);
           }
@@ -506,13 +496,17 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&x_full[g]);
       }
-      // hidden layers: X <- act(D * 2^s + b) * 2^-s', in place
+      // hidden layers: X <- act(D * 2^s + b) * 2^-s', in place.  The last hidden layer feeds the final linear
+      // layer (H -> E) directly from registers: every thread forms the partial dot products of its 32 features,
+      // the four column quarters meet in shared memory.
       for (int l = 0; l < n_hidden; ++l) {
+        const bool last = l == n_hidden - 1;
         const uint32_t bl_a = tc::smem_u32(bias_s + l * 128 + col0);
+        const uint32_t wf_a = tc::smem_u32(wf4 + col0);
         const float s_out = p.out_scale[l], s_in = p.in_scale[l + 1];
-  #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g >= n_in_pair) continue;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (g >= n_in_pair) continue;
           const long long q0 = p.dbg ? clock64() : 0;
           tc::mbar_wait(&d_full[g], pd[g]);
           if (p.dbg && warp == 2 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 3), (unsigned long long)(clock64() - q0));
@@ -520,60 +514,70 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
           tc::tc_fence_after();
           const uint32_t t_main = t_lane + (uint32_t)g * 256u + col0, t_corr = t_main + 128u;
           const uint32_t xg = xs_a + (uint32_t)g * ETC_X_BYTES + (uint32_t)cq * 16384u;
+          float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             float v[16];
-            // (explicit shared loads: a pointer carved out of the aligned buffer would compile to generic loads)
             tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
+              // (explicit shared loads: a pointer carved out of the aligned buffer would compile to generic loads)
               const float4 b0 = tc::lds128(bl_a + cc * 64 + hh * 32), b1 = tc::lds128(bl_a + cc * 64 + hh * 32 + 16);
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               float x[8];
+              if (!last) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                x[i] = act_t<ACT>(fmaf(v[hh * 8 + i], s_out, bb[i])) * s_in;
-              uint4 hi, lo;
-              tc::split8_f16(x, hi, lo);
-              const uint32_t off = xg + tc::sw64_chunk_offset(row, cc * 2 + hh);
-              tc::sts128(off, hi);
-              tc::sts128(off + 8192u, lo);
+                for (int i = 0; i < 8; ++i)
+                  x[i] = act_t<ACT>(fmaf(v[hh * 8 + i], s_out, bb[i])) * s_in;
+                uint4 hi, lo;
+                tc::split8_f16(x, hi, lo);
+                const uint32_t off = xg + tc::sw64_chunk_offset(row, cc * 2 + hh);
+                tc::sts128(off, hi);
+                tc::sts128(off + 8192u, lo);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float y = act_t<ACT>(fmaf(v[hh * 8 + i], s_out, bb[i]));
+                  const float4 w = tc::lds128(wf_a + (uint32_t)(cc * 16 + hh * 8 + i) * 16u);
+                  o0 = fmaf(y, w.x, o0);
+                  o1 = fmaf(y, w.y, o1);
+                  o2 = fmaf(y, w.z, o2);
+                  o3 = fmaf(y, w.w, o3);
+                }
+              }
             }
           }
-          tc::fence_proxy_async();
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&x_full[g]);
-        }
-      }
-      // final linear layer (columns 0..15 of the slot's accumulators) * mask
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g >= n_in_pair) continue;
-        tc::mbar_wait(&d_full[g], pd[g]);
-        pd[g] ^= 1;
-        tc::tc_fence_after();
-        if (cq == 0) {
-          float va[8], vb[8];
-          tc::tmem_ld8(t_lane + (uint32_t)g * 256u, va);
-          tc::tmem_ld8(t_lane + (uint32_t)g * 256u + 16u, vb);
-          const int64_t e = eidx[g];
-          if (e < p.n_edges) {
-            const bool m = dd[g] > 0.0f;
-            const float s_out = p.out_scale[n_hidden];
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
-            if (p.out != nullptr)
-              for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
-            if (p.rec != nullptr) {
-              const int64_t er = p.rec_k ? rec_slot(p.rec_e0 + e, p.rec_k) - p.rec_e0 : e;
-              p.rec[er] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+          if (!last) {
+            tc::fence_proxy_async();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&x_full[g]);
+          } else {
+            // final linear layer * mask (model.py:128,261): sum the four column quarters in a fixed order
+            tc::tc_fence_before();
+            part[(g * 4 + cq) * 128 + row] = make_float4(o0, o1, o2, o3);
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            if (cq == 0) {
+              const int64_t e = eidx[g];
+              if (e < p.n_edges) {
+                const float4 p0 = part[(g * 4 + 0) * 128 + row], p1 = part[(g * 4 + 1) * 128 + row];
+                const float4 p2 = part[(g * 4 + 2) * 128 + row], p3 = part[(g * 4 + 3) * 128 + row];
+                const bool m = dd[g] > 0.0f;
+                float o[4];
+                o[0] = m ? ((p0.x + p1.x) + (p2.x + p3.x)) + bf_s[0] : 0.0f;
+                o[1] = m ? ((p0.y + p1.y) + (p2.y + p3.y)) + bf_s[1] : 0.0f;
+                o[2] = m ? ((p0.z + p1.z) + (p2.z + p3.z)) + bf_s[2] : 0.0f;
+                o[3] = m ? ((p0.w + p1.w) + (p2.w + p3.w)) + bf_s[3] : 0.0f;
+                if (p.out != nullptr)
+                  for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
+                if (p.rec != nullptr) {
+                  const int64_t er = p.rec_k ? rec_slot(p.rec_e0 + e, p.rec_k) - p.rec_e0 : e;
+                  p.rec[er] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
+                }
+              }
             }
           }
         }
-        tc::tc_fence_before();
       }
     }
   }
