@@ -449,53 +449,57 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
     const uint32_t xs_a = tc::smem_u32(xs);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t pd[2] = {0, 0};
+    // pass 0 of a tile: RBF expansion * mask  (layers.py:137-140, model.py:251-257) -> operand X of slot g.
+    // It is issued for the NEXT pair's tile right after the slot's last epilogue of the current pair, so the MMA
+    // thread always has the other slot's (or the next tile's) layer to run while the CUDA cores work.
+    float dd[2] = {0.0f, 0.0f};
+    int32_t idxs[2] = {0, 0};
+    int64_t eidx[2] = {0, 0};
+    auto rbf_phase = [&](int g, int tile_n) {
+      if (tile_n >= n_my) return;
+      const int64_t tile = blockIdx.x + (int64_t)tile_n * gridDim.x;
+      const int64_t e = tile * 128 + row;
+      eidx[g] = e;
+      float d = 0.0f;
+      int32_t idx = 0;
+      if (e < p.n_edges) {
+        d = __ldg(p.edges + e);
+        if (p.nlist != nullptr && cq == 0) {
+          idx = __ldg(p.nlist + e);
+          if (idx < 0 || idx >= p.n_atoms) {
+            atomicOr(p.err_flag, 1);
+            idx = 0;
+          }
+        }
+      }
+      idxs[g] = idx;
+      dd[g] = d;
+      const bool m = d > 0.0f;
+      const float s_in = m ? p.in_scale[0] : 0.0f;
+      const uint32_t xg = xs_a + (uint32_t)g * ETC_X_BYTES + (uint32_t)cq * 16384u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float diff = d - cen_s[col0 + j * 8 + i];
+          // exp(-(d - mu)^2 / gap) = 2^(diff^2 * (-log2(e) / gap))
+          x[i] = tc::ex2_approx(diff * diff * p.rbf_c) * s_in;
+        }
+        uint4 hi, lo;
+        tc::split8_f16(x, hi, lo);
+        const uint32_t off = xg + tc::sw64_chunk_offset(row, j);
+        tc::sts128(off, hi);
+        tc::sts128(off + 8192u, lo);
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&x_full[g]);
+    };
+    rbf_phase(0, 0);
+    rbf_phase(1, 1);
     for (int pair = 0; pair * 2 < n_my; ++pair) {
       const int n_in_pair = min(2, n_my - pair * 2);
-      float dd[2];
-      int32_t idxs[2] = {0, 0};
-      int64_t eidx[2];
-      // pass 0: RBF expansion * mask  (layers.py:137-140, model.py:251-257)
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g >= n_in_pair) continue;
-        const int64_t tile = blockIdx.x + (int64_t)(pair * 2 + g) * gridDim.x;
-        const int64_t e = tile * 128 + row;
-        eidx[g] = e;
-        float d = 0.0f;
-        if (e < p.n_edges) {
-          d = __ldg(p.edges + e);
-          if (p.nlist != nullptr && cq == 0) {
-            int32_t idx = __ldg(p.nlist + e);
-            if (idx < 0 || idx >= p.n_atoms) {
-              atomicOr(p.err_flag, 1);
-              idx = 0;
-            }
-            idxs[g] = idx;
-          }
-        }
-        dd[g] = d;
-        const bool m = d > 0.0f;
-        const float s_in = m ? p.in_scale[0] : 0.0f;
-        const uint32_t xg = xs_a + (uint32_t)g * ETC_X_BYTES + (uint32_t)cq * 16384u;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float x[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float diff = d - cen_s[col0 + j * 8 + i];
-            // exp(-(d - mu)^2 / gap) = 2^(diff^2 * (-log2(e) / gap))
-            x[i] = tc::ex2_approx(diff * diff * p.rbf_c) * s_in;
-          }
-          uint4 hi, lo;
-          tc::split8_f16(x, hi, lo);
-          const uint32_t off = xg + tc::sw64_chunk_offset(row, j);
-          tc::sts128(off, hi);
-          tc::sts128(off + 8192u, lo);
-        }
-        tc::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&x_full[g]);
-      }
       // hidden layers: X <- act(D * 2^s + b) * 2^-s', in place.  The last hidden layer feeds the final linear
       // layer (H -> E) directly from registers: every thread forms the partial dot products of its 32 features,
       // the four column quarters meet in shared memory.
@@ -576,6 +580,7 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
                 }
               }
             }
+            rbf_phase(g, (pair + 1) * 2 + g);      // slot g is free (its MMAs completed before d_full): next tile
           }
         }
       }
