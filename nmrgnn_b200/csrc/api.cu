@@ -1129,7 +1129,7 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
   int n_chunks = 1;
   int64_t chunk_atoms = n_atoms;
   if (mem == NMRGNN_MEM_HOST && n_atoms >= 32768) {
-    n_chunks = 4;
+    n_chunks = n_atoms >= 131072 ? 8 : 4;    // only the first chunk's upload is not hidden behind an edge kernel
     chunk_atoms = (((n_atoms + n_chunks - 1) / n_chunks) + 127) / 128 * 128;
     n_chunks = (int)((n_atoms + chunk_atoms - 1) / chunk_atoms);
     if (n_chunks > MAX_CHUNKS) n_chunks = MAX_CHUNKS, chunk_atoms = n_atoms;
