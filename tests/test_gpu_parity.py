@@ -449,3 +449,28 @@ def test_generic_geometry_models(hp):
             m((atoms, bad, edges, inv))
     finally:
         m.close()
+
+
+def test_bad_index_detected_on_both_routes(any_model):
+    """An out-of-range neighbour index raises IndexError (TF's CPU GatherV2 raises too) on the tensor-core route
+    (index check inside the edge kernel, chunked or not) and on the exact-FP32 route; the handle stays usable."""
+    g = load_golden("prot300")
+    atoms, nlist, edges, inv = graph_of(g)
+    bad = nlist.copy()
+    bad[123, 7] = atoms.shape[0]
+    with pytest.raises(IndexError):
+        any_model((atoms, bad, edges, inv))
+    bad[123, 7] = -3
+    with pytest.raises(IndexError):
+        any_model((atoms, bad, edges, inv))
+    y = any_model((atoms, nlist, edges, inv))
+    assert tol_ratio(y, g["peaks_f64"]) <= 1.0
+    # device-tensor call: the error is deferred to synchronize()
+    import torch
+    dev = torch.device("cuda", any_model.device)
+    bad[123, 7] = 10 ** 6
+    t = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (atoms, bad, edges, inv)]
+    any_model(tuple(t))
+    with pytest.raises(IndexError):
+        any_model.synchronize()
+    any_model.synchronize()                                   # flag cleared
