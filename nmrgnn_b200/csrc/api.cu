@@ -1343,7 +1343,7 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
     if (n > max_n) max_n = n;
   }
   if (max_n == 0) return NMRGNN_OK;
-  const int64_t chunks = (max_n + KNN_THREADS - 1) / KNN_THREADS;
+  const int64_t chunks = (max_n + KNN_QPB - 1) / KNN_QPB;
   if (chunks > 65535) return fail(h, NMRGNN_ERR_BAD_DIMS, "graph of %lld atoms is too large for the kNN builder", (long long)max_n);
   Io io{h, mem, s};
   const void* d_pos;
