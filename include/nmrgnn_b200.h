@@ -141,7 +141,9 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
 /* Diagnostic: D[128,128] = A[128,64] @ W[64,128] (host buffers) on the tcgen05 building
  * blocks (K-major 64B-swizzled operands, TMEM accumulators).  mode 0 = 3xTF32 split in one
  * accumulator, mode 1 = single TF32 product, mode 2 = FP16 scaled split with main/correction
- * accumulators (the production scheme, fp32-level accuracy), mode 3 = single FP16 product. */
+ * accumulators (the production scheme, fp32-level accuracy), mode 3 = single FP16 product, mode 4 = mode 3
+ * with the A operand in tensor memory, modes 5 / 6 = mode 3 issued by a CTA pair (cta_group::2, M = 256;
+ * D = the leader's / the peer's 128 rows, the peer's copy of A rotated by one row). */
 int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float* D, int mode);
 
 /* Diagnostic: the round-toward-zero compensation constants of the tensor-core path, in units of

@@ -1228,7 +1228,7 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
   int rc = begin_call(h, NMRGNN_MEM_HOST, nullptr, &s);
   if (rc) return rc;
   if (!A || !W || !D) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
-  if (mode < 0 || mode > 4) return fail(h, NMRGNN_ERR_BAD_DIMS, "mode must be 0..4");
+  if (mode < 0 || mode > 6) return fail(h, NMRGNN_ERR_BAD_DIMS, "mode must be 0..6");
   if (!h->tc_ok) return fail(h, NMRGNN_ERR_BAD_DIMS, "tensor-core path not available for this geometry");
   std::vector<uint8_t> img;
   if (mode <= 1) pack_sw64(W, ST_K, 128, 0, 128, 128, img);
@@ -1242,6 +1242,7 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
   CUDA_TRY(h, cudaStreamSynchronize(s));  // img is a local vector
   if (mode <= 1) tc_selftest_kernel<<<1, 192, ST_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
   else if (mode == 4) tc_selftest_ts_kernel<<<1, 192, STH_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p);
+  else if (mode >= 5) tc_selftest_pair_kernel<<<2, 192, STP_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode - 5);
   else tc_selftest_f16_kernel<<<1, 192, STH_SMEM, s>>>(d_A, d_img, (float*)h->tmp_out.p, mode);
   h->launches++;
   CUDA_TRY(h, cudaMemcpyAsync(D, h->tmp_out.p, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost, s));

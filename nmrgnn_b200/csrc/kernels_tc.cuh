@@ -264,6 +264,98 @@ __global__ void __launch_bounds__(192, 1) tc_selftest_ts_kernel(const float* __r
   if (warp == 4) tc::tmem_dealloc<256>(tmem_base);
 }
 
+// modes 5 / 6: CTA pair (cta_group::2), single product fp16(A) * fp16(W): one M = 256, N = 128 instruction per K-step
+// over a cluster of two CTAs.  CTA r stages its own 128 rows of A (the peer's copy of A is rotated by one row so
+// that the test can tell the two apart) and N rows [64 r, 64 r + 64) of W; the peer reports "operands ready" on the
+// leader's barrier, the leader issues the MMAs and the commit is multicast to both CTAs.  mode 5 returns the leader's
+// 128 x 128 block of D, mode 6 the peer's.
+constexpr size_t STP_SMEM = 1024 + (size_t)STH_CHUNKS * (8192 + 4096) + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+    tc_selftest_pair_kernel(const float* __restrict__ A, const uint8_t* __restrict__ Bimg, float* __restrict__ D, int want_rank) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_hi = smem;                                  // [chunks][128 rows x 64 B]
+  uint8_t* b = a_hi + STH_CHUNKS * 8192;                 // [chunks][64 rows x 64 B]: this CTA's half of W (hi image)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b + STH_CHUNKS * 4096);
+  uint64_t* b_full = bars;
+  uint64_t* d_full = bars + 1;
+  uint64_t* peer_ready = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = tc::cluster_ctarank();
+  if (tid == 0) {
+    tc::mbar_init(b_full, 1);
+    tc::mbar_init(d_full, 1);
+    tc::mbar_init(peer_ready, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 4) tc::tmem_alloc_pair<128>(tmem_slot);
+  tc::tc_fence_before();
+  tc::cluster_sync();        // barriers of both CTAs exist before any remote arrive / multicast commit
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 5 && lane == 0) {
+    tc::mbar_expect_tx(b_full, STH_CHUNKS * 4096);
+    for (int c = 0; c < STH_CHUNKS; ++c) tc::bulk_g2s(b + c * 4096, Bimg + (size_t)c * 16384 + rank * 4096, 4096, b_full);
+  }
+  if (tid < 128) {
+    const int r = tid;
+    const int src = (r + (int)rank) & 127;
+    for (int c = 0; c < STH_CHUNKS; ++c) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x[8];
+        const float4 x0 = *reinterpret_cast<const float4*>(A + src * ST_K + c * tc::HK + j * 8);
+        const float4 x1 = *reinterpret_cast<const float4*>(A + src * ST_K + c * tc::HK + j * 8 + 4);
+        x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w;
+        x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        uint4 hi, lo;
+        tc::split8_f16(x, hi, lo);
+        *reinterpret_cast<uint4*>(a_hi + c * 8192 + tc::sw64_chunk_offset(r, j)) = hi;
+      }
+    }
+    tc::fence_proxy_async();
+  }
+  __syncthreads();
+  if (rank == 1 && warp == 5 && lane == 0) {
+    tc::mbar_wait(b_full, 0);
+    tc::mbar_arrive_cluster(tc::map_to_cta(tc::smem_u32(peer_ready), 0));
+  }
+  if (rank == 0 && warp == 4 && lane == 0) {
+    tc::mbar_wait(b_full, 0);
+    tc::mbar_wait_cluster(peer_ready, 0);
+    tc::tc_fence_after();
+    const uint32_t idesc = tc::make_idesc_f16(256, 128);
+    for (int c = 0; c < STH_CHUNKS; ++c) {
+      const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(a_hi + c * 8192));
+      const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(b + c * 4096));
+#pragma unroll
+      for (int ks = 0; ks < tc::HK / tc::UMMA_K_F16; ++ks) {
+        const uint64_t adv = (uint64_t)(ks * tc::UMMA_K_F16 * 2) >> 4;
+        tc::umma_f16_pair(tmem_base, ah + adv, bh + adv, idesc, (c | ks) != 0);
+      }
+    }
+    tc::umma_commit_pair(d_full, 3);
+  }
+  if (tid < 128) {
+    tc::mbar_wait(d_full, 0);
+    tc::tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < 8; ++c) {
+      float v[16];
+      tc::tmem_ld16(lane_base + c * 16, v);
+      if ((int)rank == want_rank) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[tid * 128 + c * 16 + i] = v[i];
+      }
+    }
+    tc::tc_fence_before();
+  }
+  tc::cluster_sync();        // both CTAs have drained their accumulators
+  if (warp == 4) tc::tmem_dealloc_pair<128>(tmem_base);
+}
+
 // ----------------------------------------------------------------------------------
 // Edge MLP on tensor cores (RBF -> EdgeFCBlock -> mask; model.py:251-261).
 // One CTA keeps TWO 128-edge tiles in flight (slots 0/1) so that the CUDA-core epilogue

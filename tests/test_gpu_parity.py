@@ -310,6 +310,12 @@ def test_tcgen05_selftest_gemm(model):
     assert f1 < 5e-3, "kind::f16 GEMM structurally wrong (layout/descriptor)"
     assert f3 < 1e-6, "fp16 scaled split does not reach fp32-level accuracy"
     assert f1 > 20 * f3
+    # the same single product by a CTA pair (cta_group::2, M = 256 over two CTAs, each staging half of W):
+    # bit-identical to the one-CTA instruction; the peer's copy of A is rotated by one row
+    p0 = model.handle.selftest_gemm(A, W, 5)
+    p1 = model.handle.selftest_gemm(A, W, 6)
+    assert np.array_equal(p0, h1), "cta_group::2: leader's accumulator differs from the one-CTA product"
+    assert np.array_equal(p1, np.roll(h1, -1, axis=0)), "cta_group::2: peer's accumulator is not the peer's rows"
 
 
 # ---------------------------------------------------------------------------------------------------
