@@ -160,6 +160,9 @@ int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap);
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "edge_ts" = 1: edge MLP with its activation operand in tensor memory (TS-form tcgen05.mma; bit-identical
  *                  output, measured slower than the default SS form; kept for comparison);
+ *   "mp_pair" = 1: MP layers as CTA pairs (cta_group::2: one M = 256 instruction stream per two neighbouring
+ *                  128-atom tiles, each CTA staging half of W'; bit-identical output; measured 5 % slower than the
+ *                  one-CTA form on B200, kept as the base of the next round's work);
  *   "mp_role_counters" = 1 / 2 / 0: diagnostics -- arm per-CTA cycle counters of the warp roles of the next MP-layer
  *                  or edge launch / print their means to stdout / disarm;
  *   "profile"    = 1: nmrgnn_forward records CUDA events (on the launching stream) around its

@@ -83,6 +83,7 @@ struct nmrgnn_handle {
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
   bool compensate = true;
+  bool mp_pair = false;                 // option "mp_pair": the CTA-pair (cta_group::2) form of the MP-layer kernel
   bool edge_ts = false;                 // option "edge_ts": the TS-form edge kernel (activation operand in tensor memory)
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
@@ -530,7 +531,14 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.swz = rec_swizzled(K) ? 1 : 0;
   a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
-  ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+  if (h->mp_pair) {
+    // CTA pairs: one cluster of two CTAs per pair of neighbouring tiles (cta_group::2)
+    const int64_t pairs = (tiles + 1) / 2;
+    const int clusters = (int)std::min<int64_t>(pairs, h->num_sms / 2);
+    ACT_DISPATCH(a.act, mp_layer_pair_kernel, 2 * clusters, MTC_THREADS, MTC_PAIR_SMEM, s, a);
+  } else {
+    ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+  }
   h->launches++;
   return NMRGNN_OK;
 }
@@ -931,6 +939,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
       TRY_RC(upload_bytes(h, img.data(), img.size(), &h->mp_img[l]));
     }
     ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
+    ACT_SET_SMEM(mp_layer_pair_kernel, MTC_PAIR_SMEM);
     h->mp_corr.assign(dims->n_mp, 1.0f);
     TRY_RC(calibrate_mp(h));
     h->launches = 0;
@@ -1303,6 +1312,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
                n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[5] / n, m[6] / n);
     }
     if (value == 0) h->mp_dbg = nullptr;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_pair") == 0) {
+    h->mp_pair = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "edge_ts") == 0) {

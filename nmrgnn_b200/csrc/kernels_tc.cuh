@@ -1048,22 +1048,37 @@ constexpr int MTC_KMAX = 16;
 // 64-byte-swizzled tiles need a 512-byte aligned base
 constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * 32768 + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 static_assert(MTC_SMEM <= 227 * 1024, "MP tensor-core kernel exceeds the 227 KB shared-memory limit");
+// CTA-pair form (cta_group::2): two CTAs of a cluster work on two neighbouring 128-atom tiles with ONE M = 256
+// instruction stream issued by the leader (rank 0).  Each CTA stages only its half of W' (N rows 128 r .. 128 r + 127 of
+// the hi and lo images: 16 KB per (pass, n) chunk instead of 32 KB), so the tensor core reads half as many B-operand
+// bytes from each SM's shared memory and the bulk copies write half as many — the MP layer is bound by that data
+// pipe.  Hand-offs that cross the pair: the producers and the epilogue warps of both CTAs arrive on the
+// LEADER's a_full / d_empty barriers (cluster-scope release), the peer's idle MMA warp relays "my half of W' has
+// landed" to the leader's b_peer barriers, and the leader's commits are multicast to both CTAs.
+constexpr int MTC_PAIR_BRING = 3;
+constexpr int MTC_PAIR_BSLOT = 16384;
+constexpr int MTC_PAIR_ASTAGES = 3;    // the halved W' ring pays for a third operand stage: the two CTAs of a pair decouple
+constexpr size_t MTC_PAIR_SMEM = 512 + MTC_PAIR_ASTAGES * 3 * 16384 + MTC_PAIR_BRING * MTC_PAIR_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 
-template <int ACT>
-__global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
+template <int ACT, bool PAIR>
+__device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
+  constexpr int BRING = PAIR ? MTC_PAIR_BRING : MTC_BRING;
+  constexpr int BSLOT = PAIR ? MTC_PAIR_BSLOT : 32768;
+  constexpr uint32_t AST = PAIR ? MTC_PAIR_ASTAGES : 2;      // operand stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~uintptr_t(511));
   uint8_t* a_st = smem;                                   // [2 stages][3 chunks][hi 8192 | lo 8192]
-  uint8_t* b_ring = a_st + 2 * 3 * 16384;                 // [BRING][hi 16384 | lo 16384]
-  float4* rec_s = reinterpret_cast<float4*>(b_ring + MTC_BRING * 32768);   // [128 * K]
+  uint8_t* b_ring = a_st + AST * 3 * 16384;                 // [BRING][hi 16384 | lo 16384]
+  float4* rec_s = reinterpret_cast<float4*>(b_ring + BRING * BSLOT);       // [128 * K]
   float* fscale = reinterpret_cast<float*>(rec_s + 128 * MTC_KMAX);        // [2][128]  2^-s
   float* oscale = fscale + 2 * 128;                                         // [2][128]  2^s * inv_degree * corr
   uint64_t* bars = reinterpret_cast<uint64_t*>(oscale + 2 * 128);
   uint64_t* a_full = bars;            // [2]
-  uint64_t* a_empty = a_full + 2;     // [2]
-  uint64_t* b_full = a_empty + 2;     // [BRING]
-  uint64_t* b_empty = b_full + MTC_BRING;
-  uint64_t* rec_full = b_empty + MTC_BRING;
+  uint64_t* a_empty = a_full + AST;   // [AST]
+  uint64_t* b_full = a_empty + AST;   // [BRING]
+  uint64_t* b_empty = b_full + BRING;
+  uint64_t* b_peer = b_empty + BRING; // [BRING]  (pair, leader: the peer's half of the slot has landed)
+  uint64_t* rec_full = b_peer + BRING;
   uint64_t* rec_empty = rec_full + 1;
   uint64_t* d_full = rec_empty + 1;
   uint64_t* d_empty = d_full + 1;
@@ -1071,40 +1086,59 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&a_full[i], 8);
+    for (int i = 0; i < (int)AST; ++i) {
+      tc::mbar_init(&a_full[i], PAIR ? 16 : 8);      // pair: the producer warps of both CTAs
       tc::mbar_init(&a_empty[i], 1);
-      tc::mbar_init(&sc_full[i], 8);
     }
-    for (int i = 0; i < MTC_BRING; ++i) {
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&sc_full[i], 8);
+    for (int i = 0; i < BRING; ++i) {
       tc::mbar_init(&b_full[i], 1);
       tc::mbar_init(&b_empty[i], 1);
+      tc::mbar_init(&b_peer[i], 1);
     }
     tc::mbar_init(rec_full, 1);
     tc::mbar_init(rec_empty, 8);
     tc::mbar_init(d_full, 1);
-    tc::mbar_init(d_empty, 4);
+    tc::mbar_init(d_empty, PAIR ? 8 : 4);            // pair: the epilogue warps of both CTAs
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tc::tmem_alloc_pair<512>(tmem_slot);
+    else tc::tmem_alloc<512>(tmem_slot);
+  }
   tc::tc_fence_before();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync();     // both CTAs' barriers exist before any remote arrive / multicast commit
+  else __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int K = p.K, E = p.E;
   const int64_t n_tiles = (p.n_atoms + 127) / 128;
+  // tile walk: a single CTA takes tiles blockIdx.x, + gridDim.x, ...; a pair takes tile pairs and CTA r the r-th
+  // tile of each pair (a trailing odd tile leaves the peer with an empty tile: it still runs the whole protocol)
+  const int64_t tile_first = PAIR ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
+  const int64_t tile_step = PAIR ? (int64_t)gridDim.x : (int64_t)gridDim.x;
+  const int64_t tile_end = PAIR ? ((n_tiles + 1) / 2) * 2 : n_tiles;
+  // the leader's barriers as seen from either CTA of the pair
+  const uint32_t a_full_ldr = PAIR ? tc::map_to_cta(tc::smem_u32(a_full), 0) : 0u;
+  const uint32_t d_empty_ldr = PAIR ? tc::map_to_cta(tc::smem_u32(d_empty), 0) : 0u;
 
   if (warp == 0) {
     // ===================== W' loader =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
         for (int q = 0; q < MTC_PASSES * E; ++q, ++it) {
-          const uint32_t slot = it % MTC_BRING, ph = (it / MTC_BRING) & 1;
+          const uint32_t slot = it % BRING, ph = (it / BRING) & 1;
           tc::mbar_wait_relaxed(&b_empty[slot], ph ^ 1);
-          tc::mbar_expect_tx(&b_full[slot], 32768);
-          tc::bulk_g2s(b_ring + slot * 32768, p.Wimg + (size_t)q * 32768, 32768, &b_full[slot]);
+          tc::mbar_expect_tx(&b_full[slot], BSLOT);
+          if (PAIR) {   // this CTA's 128 N rows of the hi and of the lo image
+            tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * 32768 + rank * 8192, 8192, &b_full[slot]);
+            tc::bulk_g2s(b_ring + slot * BSLOT + 8192, p.Wimg + (size_t)q * 32768 + 16384 + rank * 8192, 8192, &b_full[slot]);
+          } else {
+            tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * 32768, 32768, &b_full[slot]);
+          }
         }
     }
   } else if (warp == 2) {
@@ -1114,17 +1148,17 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
     // most neighbours live), so that the gathers of the next tile hit L2 instead of paying DRAM latency
     // on the producers' critical path.  Pure hint: no effect on results.
     uint32_t t = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       if (lane == 0) {
         const int64_t a0 = tile * 128;
-        const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+        const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
         const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 16u;
         tc::mbar_wait_relaxed(rec_empty, (t & 1) ^ 1);
         tc::mbar_expect_tx(rec_full, bytes);
-        tc::bulk_g2s(rec_s, p.rec + a0 * K, bytes, rec_full);
+        if (bytes) tc::bulk_g2s(rec_s, p.rec + a0 * K, bytes, rec_full);
       }
       __syncwarp();
-      const int64_t nt = tile + gridDim.x;
+      const int64_t nt = tile + tile_step;
       if (nt < n_tiles) {
         const int64_t b0 = nt * 128;
         const int nrows = (int)min((int64_t)128, p.n_atoms - b0);
@@ -1134,49 +1168,73 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
         for (int i = lane; i * 128 < nrows * K * 16; i += 32) tc::prefetch_l2(rb + (size_t)i * 128);
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ===================== peer CTA: relay "my half of the W' slot has landed" to the leader =====================
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(128, 256);
+      const uint32_t b_peer_ldr = tc::map_to_cta(tc::smem_u32(b_peer), 0);
+      uint32_t it = 0;
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
+        for (int q = 0; q < MTC_PASSES * E; ++q, ++it) {
+          const uint32_t slot = it % BRING;
+          tc::mbar_wait(&b_full[slot], (it / BRING) & 1);
+          tc::mbar_arrive_cluster(b_peer_ldr + slot * 8u);
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_f16(PAIR ? 256 : 128, 256);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
       uint32_t it = 0, pass = 0, t = 0;
       long long w_d = 0, w_a = 0, w_b = 0, c0 = 0;
       const long long k0 = clock64();
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
         if (p.dbg) c0 = clock64();
-        tc::mbar_wait(d_empty, (t & 1) ^ 1);      // epilogue has drained the previous tile's accumulators
+        if (PAIR) tc::mbar_wait_cluster(d_empty, (t & 1) ^ 1);   // both epilogues have drained their accumulators
+        else tc::mbar_wait(d_empty, (t & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
         if (p.dbg) w_d += clock64() - c0;
         tc::tc_fence_after();
         for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
-          const uint32_t st = pass & 1;
+          const uint32_t st = pass % AST;
           if (p.dbg) c0 = clock64();
-          tc::mbar_wait(&a_full[st], (pass >> 1) & 1);
+          if (PAIR) tc::mbar_wait_cluster(&a_full[st], (pass / AST) & 1);
+          else tc::mbar_wait(&a_full[st], (pass / AST) & 1);
           if (p.dbg) w_a += clock64() - c0;
           tc::tc_fence_after();
           for (int n = 0; n < E; ++n, ++it) {
-            const uint32_t slot = it % MTC_BRING;
+            const uint32_t slot = it % BRING;
             if (p.dbg) c0 = clock64();
-            tc::mbar_wait(&b_full[slot], (it / MTC_BRING) & 1);
+            tc::mbar_wait(&b_full[slot], (it / BRING) & 1);
+            if (PAIR) tc::mbar_wait_cluster(&b_peer[slot], (it / BRING) & 1);
             if (p.dbg) w_b += clock64() - c0;
             tc::tc_fence_after();
             const uint8_t* ac = a_st + (st * 3 + n) * 16384;
             const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(ac));
             const uint64_t al = tc::make_desc_sw64(tc::smem_u32(ac + 8192));
-            const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * 32768));
-            const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * 32768 + 16384));
+            const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * BSLOT));
+            const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * BSLOT + BSLOT / 2));
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
               const uint32_t acc = (ps | n | ks) != 0;
-              tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
-              tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc);
-              tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+              if (PAIR) {
+                tc::umma_f16_pair(d_main, ah + adv, bh + adv, idesc, acc);
+                tc::umma_f16_pair(d_corr, al + adv, bh + adv, idesc, acc);
+                tc::umma_f16_pair(d_corr, ah + adv, bl + adv, idesc, 1);
+              } else {
+                tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc);
+                tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+              }
             }
-            tc::umma_commit(&b_empty[slot]);
+            if (PAIR) tc::umma_commit_pair(&b_empty[slot], 3);
+            else tc::umma_commit(&b_empty[slot]);
           }
-          tc::umma_commit(&a_empty[st]);
+          if (PAIR) tc::umma_commit_pair(&a_empty[st], 3);
+          else tc::umma_commit(&a_empty[st]);
         }
-        tc::umma_commit(d_full);
+        if (PAIR) tc::umma_commit_pair(d_full, 3);
+        else tc::umma_commit(d_full);
       }
       if (p.dbg) {
         long long* o = p.dbg + (size_t)blockIdx.x * 8;
@@ -1199,16 +1257,16 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
     const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_corr = t_main + 256u;
     uint32_t t = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
-      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));   // 0: the pair's trailing empty tile
       tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
       const float osc = oscale[(t & 1) * 128 + row];
       // rows grow .. grow+7 of this group, clamped for the loads (stores are predicated)
-      const float* hin = p.h_in + (a0 + min(grow, rows - 1)) * 256 + gi * 4;
+      const float* hin = p.h_in + (rows > 0 ? a0 + min(grow, rows - 1) : 0) * 256 + gi * 4;
       float* hout = p.h_out + (a0 + grow) * 256 + gi * 4;
       // (rows past the end of a partial tile re-read the tile's last row; their stores are predicated off)
-      const int rlast = rows - 1 - min(grow, rows - 1);
+      const int rlast = rows > 0 ? rows - 1 - min(grow, rows - 1) : 0;
       float4 res[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) res[k] = p.raw ? make_float4(0.f, 0.f, 0.f, 0.f) : tc::ldg128(hin + min(k, rlast) * 256);
@@ -1267,7 +1325,10 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(d_empty);
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_cluster(d_empty_ldr);
+        else tc::mbar_arrive(d_empty);
+      }
       if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
       // row maxima: reduce over the 8 lanes of the group, lane k writes row grow + k
       float mine = 0.0f;
@@ -1291,9 +1352,9 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
     const uint32_t ast_a = tc::smem_u32(a_st);
     const float* hq = p.h_in + q8 * 4;
     uint32_t pass = 0, t = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+    for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
-      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
       float* fs = fscale + (t & 1) * 128;
       float* os = oscale + (t & 1) * 128;
       const uint32_t fs_a = tc::smem_u32(fs);
@@ -1382,9 +1443,9 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
       if (lane == 0) tc::mbar_arrive(&sc_full[t & 1]);
 
       for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
-        const uint32_t st = pass & 1;
+        const uint32_t st = pass % AST;
         const long long p0 = p.dbg ? clock64() : 0;
-        tc::mbar_wait(&a_empty[st], ((pass >> 1) & 1) ^ 1);
+        tc::mbar_wait(&a_empty[st], ((pass / AST) & 1) ^ 1);
         if (p.dbg && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 5), (unsigned long long)(clock64() - p0));
         const uint32_t ab = ast_a + st * 3 * 16384;
 #pragma unroll 1
@@ -1431,15 +1492,31 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&a_full[st]);
+        if (lane == 0) {
+          if (PAIR) tc::mbar_arrive_cluster(a_full_ldr + st * 8u);
+          else tc::mbar_arrive(&a_full[st]);
+        }
       }
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(rec_empty);
     }
   }
   tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+  if (PAIR) tc::cluster_sync();     // the leader's MMAs read the peer's shared memory until the very end
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tc::tmem_dealloc_pair<512>(tmem_base);
+    else tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
+  mp_layer_tc_body<ACT, false>(p);
+}
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MTC_THREADS, 1) mp_layer_pair_kernel(const MpTcArgs p) {
+  mp_layer_tc_body<ACT, true>(p);
 }
 
 }  // namespace nmr

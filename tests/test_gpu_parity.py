@@ -362,6 +362,39 @@ def test_config2_full_size_properties(model, config2_batch):
     assert np.array_equal(ShardedModel(model)(config2_batch), y_tc)
 
 
+def test_mp_layer_cta_pair_form_is_bit_identical(config2_batch):
+    """Option "mp_pair": the MP layers as CTA pairs (cta_group::2, M = 256 per instruction, each CTA staging half of
+    W').  Same products in the same order, so the peaks must equal the one-CTA kernel's bit for bit — for an even
+    and an odd number of 128-atom tiles (the odd one leaves the peer CTA of the last pair with an empty tile)."""
+    import nmrgnn_b200
+    from nmrgnn_b200.workloads import take_graphs
+    m = nmrgnn_b200.load_model()
+    try:
+        m.handle.set_option("tc_min_atoms", 0)
+        offs = config2_batch[4]
+        cases = [take_graphs(config2_batch, np.array([0])), take_graphs(config2_batch, np.array([1, 2, 3])), config2_batch]
+        parities = set()
+        for g in cases:
+            n = g[0].shape[0]
+            parities.add(((n + 127) // 128) & 1)
+            m.handle.set_option("mp_pair", 0)
+            y0 = m(g[:4])
+            m.handle.set_option("mp_pair", 1)
+            y1 = m(g[:4])
+            assert m.handle.compute_path.startswith("tcgen05")
+            assert np.array_equal(y0, y1), n
+        # a graph cut to an odd / even number of tiles so that both parities are always covered
+        for n in (128 * 9 + 5, 128 * 10):
+            a, nl, e, inv = (x[:n] for x in config2_batch[:4])
+            nl = np.where(nl < n, nl, 0).astype(nl.dtype)
+            m.handle.set_option("mp_pair", 0)
+            y0 = m((a, nl, e, inv))
+            m.handle.set_option("mp_pair", 1)
+            assert np.array_equal(m((a, nl, e, inv)), y0), n
+    finally:
+        m.close()
+
+
 def test_config3_small_molecules_full_size(model):
     """configs[2]: 1024 small molecules, K = 8 (~41 k atoms): both paths run and agree on well-conditioned peaks."""
     from nmrgnn_b200 import workloads
