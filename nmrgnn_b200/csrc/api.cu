@@ -939,6 +939,11 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
       TRY_RC(upload_bytes(h, img.data(), img.size(), &h->mp_img[l]));
     }
     ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
+    // 196 KB of shared memory, 60 KB of L1 for the gathers (see MTC_SMEM)
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     ACT_SET_SMEM(mp_layer_pair_kernel, MTC_PAIR_SMEM);
     h->mp_corr.assign(dims->n_mp, 1.0f);
     TRY_RC(calibrate_mp(h));

@@ -1015,7 +1015,7 @@ __global__ void __launch_bounds__(256) row_absmax256_kernel(const float* __restr
 // The producers build T pass by pass (one pass = 32 input features x E = E operand chunks of
 // 32 k), scale each row by a power of two from an a-priori bound (fp16 range), split it into
 // the hi/lo operand tiles and hand it to the MMA warp through a 2-pass ring; W' streams
-// through a 3-slot ring of 32 KB bulk copies.  T never reaches HBM.
+// through a 4-slot ring of 16 KB bulk copies (hi and lo images separately).  T never reaches HBM.
 // The gather is the critical resource: every producer thread keeps 8-16 independent 16-byte
 // row loads in flight (two register buffers of 8, the next half-step is issued before the
 // current one is consumed, across step and pass boundaries), loads are unconditional (padded
@@ -1043,11 +1043,14 @@ struct MpTcArgs {
 
 constexpr int MTC_THREADS = 512;
 constexpr int MTC_PASSES = 8;          // 256 / 32
-constexpr int MTC_BRING = 3;
+constexpr int MTC_BRING = 4;           // W' ring: slots of 16 KB, the hi and the lo image of a (pass, n) chunk are separate slots
+constexpr int MTC_BSLOT = 16384;
 constexpr int MTC_KMAX = 16;
-// 64-byte-swizzled tiles need a 512-byte aligned base
-constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * 32768 + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
-static_assert(MTC_SMEM <= 227 * 1024, "MP tensor-core kernel exceeds the 227 KB shared-memory limit");
+// 64-byte-swizzled tiles need a 512-byte aligned base.  The kernel stays below 196 KB so that the SM can be
+// configured with 60 KB of L1 (228 KB of shared memory would leave 28 KB): the neighbour rows gathered for one
+// feature pass (~38 KB unique per tile) then mostly hit L1.
+constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * MTC_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
+static_assert(MTC_SMEM + 1024 <= 196 * 1024, "MP tensor-core kernel no longer fits the 196 KB shared-memory configuration");
 // CTA-pair form (cta_group::2): two CTAs of a cluster work on two neighbouring 128-atom tiles with ONE M = 256
 // instruction stream issued by the leader (rank 0).  Each CTA stages only its half of W' (N rows 128 r .. 128 r + 127 of
 // the hi and lo images: 16 KB per (pass, n) chunk instead of 32 KB), so the tensor core reads half as many B-operand
@@ -1063,7 +1066,8 @@ constexpr size_t MTC_PAIR_SMEM = 512 + MTC_PAIR_ASTAGES * 3 * 16384 + MTC_PAIR_B
 template <int ACT, bool PAIR>
 __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   constexpr int BRING = PAIR ? MTC_PAIR_BRING : MTC_BRING;
-  constexpr int BSLOT = PAIR ? MTC_PAIR_BSLOT : 32768;
+  constexpr int BSLOT = PAIR ? MTC_PAIR_BSLOT : MTC_BSLOT;
+  constexpr bool SPLIT = !PAIR;     // one slot = one image (hi or lo) of a chunk; pair: this CTA's halves of both
   constexpr uint32_t AST = PAIR ? MTC_PAIR_ASTAGES : 2;      // operand stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~uintptr_t(511));
@@ -1129,11 +1133,13 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
-        for (int q = 0; q < MTC_PASSES * E; ++q, ++it) {
+        for (int q = 0; q < MTC_PASSES * E * (SPLIT ? 2 : 1); ++q, ++it) {
           const uint32_t slot = it % BRING, ph = (it / BRING) & 1;
           tc::mbar_wait_relaxed(&b_empty[slot], ph ^ 1);
           tc::mbar_expect_tx(&b_full[slot], BSLOT);
-          if (PAIR) {   // this CTA's 128 N rows of the hi and of the lo image
+          if (SPLIT) {  // [pass][n][hi | lo] is contiguous in 16 KB images
+            tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * BSLOT, BSLOT, &b_full[slot]);
+          } else if (PAIR) {   // this CTA's 128 N rows of the hi and of the lo image
             tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * 32768 + rank * 8192, 8192, &b_full[slot]);
             tc::bulk_g2s(b_ring + slot * BSLOT + 8192, p.Wimg + (size_t)q * 32768 + 16384 + rank * 8192, 8192, &b_full[slot]);
           } else {
@@ -1202,7 +1208,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           if (p.dbg) w_a += clock64() - c0;
           tc::tc_fence_after();
           for (int n = 0; n < E; ++n, ++it) {
-            const uint32_t slot = it % BRING;
+            uint32_t slot = it % BRING;
             if (p.dbg) c0 = clock64();
             tc::mbar_wait(&b_full[slot], (it / BRING) & 1);
             if (PAIR) tc::mbar_wait_cluster(&b_peer[slot], (it / BRING) & 1);
@@ -1212,7 +1218,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
             const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(ac));
             const uint64_t al = tc::make_desc_sw64(tc::smem_u32(ac + 8192));
             const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * BSLOT));
-            const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * BSLOT + BSLOT / 2));
+            // products against the hi image of W': main = hi * hi, corr = lo * hi
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
@@ -1220,12 +1226,30 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
               if (PAIR) {
                 tc::umma_f16_pair(d_main, ah + adv, bh + adv, idesc, acc);
                 tc::umma_f16_pair(d_corr, al + adv, bh + adv, idesc, acc);
-                tc::umma_f16_pair(d_corr, ah + adv, bl + adv, idesc, 1);
               } else {
                 tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
                 tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc);
-                tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
               }
+            }
+            uint64_t bl;
+            if (SPLIT) {     // the lo image is the next slot of the ring
+              tc::umma_commit(&b_empty[slot]);
+              ++it;
+              slot = it % BRING;
+              if (p.dbg) c0 = clock64();
+              tc::mbar_wait(&b_full[slot], (it / BRING) & 1);
+              if (p.dbg) w_b += clock64() - c0;
+              tc::tc_fence_after();
+              bl = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * BSLOT));
+            } else {
+              bl = tc::make_desc_sw64(tc::smem_u32(b_ring + slot * BSLOT + BSLOT / 2));
+            }
+            // corr += hi * lo
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              if (PAIR) tc::umma_f16_pair(d_corr, ah + adv, bl + adv, idesc, 1);
+              else tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
             }
             if (PAIR) tc::umma_commit_pair(&b_empty[slot], 3);
             else tc::umma_commit(&b_empty[slot]);
