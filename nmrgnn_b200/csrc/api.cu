@@ -83,6 +83,7 @@ struct nmrgnn_handle {
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
   bool compensate = true;
+  bool fc_pair = false;                 // option "fc_pair": the CTA-pair (cta_group::2) form of the node-MLP kernel
   bool mp_pair = false;                 // option "mp_pair": the CTA-pair (cta_group::2) form of the MP-layer kernel
   bool edge_ts = false;                 // option "edge_ts": the TS-form edge kernel (activation operand in tensor memory)
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
@@ -590,7 +591,12 @@ int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float*
     t.peak_std = h->peak_std;
     t.peak_avg = h->peak_avg;
     const int64_t tiles = (n + 127) / 128;
-    ACT_DISPATCH(t.act, fc_readout_tc_kernel, grid_for(h, tiles, 1), FTC_THREADS, FTC_SMEM, s, t);
+    if (h->fc_pair) {
+      const int clusters = (int)std::min<int64_t>((tiles + 1) / 2, h->num_sms / 2);
+      ACT_DISPATCH(t.act, fc_readout_pair_kernel, 2 * clusters, FTC_THREADS, FTC_SMEM, s, t);
+    } else {
+      ACT_DISPATCH(t.act, fc_readout_tc_kernel, grid_for(h, tiles, 1), FTC_THREADS, FTC_SMEM, s, t);
+    }
     h->launches++;
     return NMRGNN_OK;
   }
@@ -992,6 +998,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(upload(h, bias.data(), bias.size(), &h->fc_bias));
     h->fc_rz = 1.0f + 0.17f * (float)(F / 16 + 1) / 16777216.0f;
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
+    ACT_SET_SMEM(fc_readout_pair_kernel, FTC_SMEM);
   }
   h->path = h->fast_path ? "ffma" : "generic-fp32";
   if (h->tc_ok) {
@@ -1317,6 +1324,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
                n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[5] / n, m[6] / n);
     }
     if (value == 0) h->mp_dbg = nullptr;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "fc_pair") == 0) {
+    h->fc_pair = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_pair") == 0) {

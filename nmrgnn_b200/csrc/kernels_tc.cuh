@@ -1590,8 +1590,18 @@ constexpr size_t FTC_SMEM = 1024 + FTC_X_BYTES + FTC_RING * 16384 + MAX_DENSE * 
 static_assert(FTC_SMEM <= 227 * 1024, "node-MLP tensor-core kernel exceeds the 227 KB shared-memory limit");
 static_assert(128 * FTC_LDZ * 4 <= FTC_X_BYTES, "Z overlays the X operand");
 
-template <int ACT>
-__global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcTcArgs p) {
+// CTA-pair form (cta_group::2, option "fc_pair"): two CTAs work on two neighbouring tiles with one M = 256 instruction
+// stream issued by the leader.  The B operand of a pair is split by N rows between the CTAs, and the merged
+// operand [w_hi | w_lo] splits exactly into w_hi (leader) and w_lo (peer): a slot is 12 KB per CTA —
+//   [0, 8 KB): the CTA's 128 rows of [w_hi | w_lo]    [8 KB, 12 KB): its 64 rows of w_hi for the x_lo * w_hi product
+// — and each MMA phase (the part the epilogue cannot overlap) serves two tiles.  Hand-offs across the pair as in
+// the MP pair kernel: worker warps of both CTAs arrive on the leader's x_full, the peer's idle MMA warp relays its
+// w_full, the leader's commits are multicast.
+constexpr int FTC_PAIR_SLOT = 12288;
+
+template <int ACT, bool PAIR>
+__device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
+  constexpr int SLOT = PAIR ? FTC_PAIR_SLOT : 16384;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xs = smem;                                      // [8 chunks][hi 8192 | lo 8192]; later Z [128][FTC_LDZ] fp32
@@ -1601,56 +1611,91 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
   uint64_t* bars = reinterpret_cast<uint64_t*>(rs + MAX_DENSE * 128);
   uint64_t* w_full = bars;                                 // [RING]
   uint64_t* w_empty = w_full + FTC_RING;                   // [RING]
-  uint64_t* x_full = w_empty + FTC_RING;
+  uint64_t* w_peer = w_empty + FTC_RING;                   // [RING]  (pair, leader: the peer's slot has landed)
+  uint64_t* x_full = w_peer + FTC_RING;
   uint64_t* d_full = x_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
   if (tid == 0) {
     for (int i = 0; i < FTC_RING; ++i) {
       tc::mbar_init(&w_full[i], 1);
       tc::mbar_init(&w_empty[i], 1);
+      tc::mbar_init(&w_peer[i], 1);
     }
-    tc::mbar_init(x_full, 16);
+    tc::mbar_init(x_full, PAIR ? 32 : 16);               // pair: the worker warps of both CTAs
     tc::mbar_init(d_full, 1);
     tc::mbar_fence_init();
   }
   const int nl = p.n_layers;
   for (int i = tid; i < nl * 256; i += FTC_THREADS) bias_s[i] = p.bias[i];
-  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (PAIR) tc::tmem_alloc_pair<512>(tmem_slot);
+    else tc::tmem_alloc<512>(tmem_slot);
+  }
   tc::tc_fence_before();
-  __syncthreads();
+  if (PAIR) tc::cluster_sync();
+  else __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int64_t n_tiles = (p.n_atoms + 127) / 128;
+  // tile walk (see mp_layer_tc_body): a pair takes tile pairs, CTA r the r-th tile; a trailing odd tile leaves the
+  // peer with an empty tile and the whole protocol still runs
+  const int64_t tile_first = PAIR ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
+  const int64_t tile_step = (int64_t)gridDim.x;
+  const int64_t tile_end = PAIR ? ((n_tiles + 1) / 2) * 2 : n_tiles;
+  const uint32_t x_full_ldr = PAIR ? tc::map_to_cta(tc::smem_u32(x_full), 0) : 0u;
 
   if (warp == 0) {
     // ===================== W loader =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
         for (int l = 0; l < nl; ++l) {
           const int n_slots = (l == nl - 1) ? 8 : 16;
           const uint8_t* src = p.Wimg + (size_t)l * 16 * 16384;
           for (int q = 0; q < n_slots; ++q, ++it) {
             const uint32_t slot = it % FTC_RING, ph = (it / FTC_RING) & 1;
             tc::mbar_wait(&w_empty[slot], ph ^ 1);
-            tc::mbar_expect_tx(&w_full[slot], 16384);
-            tc::bulk_g2s(ring + slot * 16384, src + (size_t)q * 16384, 16384, &w_full[slot]);
+            tc::mbar_expect_tx(&w_full[slot], SLOT);
+            if (PAIR) {
+              // leader: w_hi and its rows 0..63 again; peer: w_lo and rows 64..127 of w_hi
+              tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * 16384 + rank * 8192, 8192, &w_full[slot]);
+              tc::bulk_g2s(ring + slot * SLOT + 8192, src + (size_t)q * 16384 + rank * 4096, 4096, &w_full[slot]);
+            } else {
+              tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * 16384, 16384, &w_full[slot]);
+            }
+          }
+        }
+    }
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ===================== peer CTA: relay "my slot has landed" to the leader =====================
+    if (lane == 0) {
+      const uint32_t w_peer_ldr = tc::map_to_cta(tc::smem_u32(w_peer), 0);
+      uint32_t it = 0;
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
+        for (int l = 0; l < nl; ++l) {
+          const int n_slots = (l == nl - 1) ? 8 : 16;
+          for (int q = 0; q < n_slots; ++q, ++it) {
+            const uint32_t slot = it % FTC_RING;
+            tc::mbar_wait(&w_full[slot], (it / FTC_RING) & 1);
+            tc::mbar_arrive_cluster(w_peer_ldr + slot * 8u);
           }
         }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
     if (lane == 0) {
       // per 128-column half h: tensor-memory columns [256h, 256h+128) = main, [256h+128, 256h+256) = corr, so that
       // x_hi * [w_hi | w_lo] -> [main | corr] is ONE N = 256 instruction (the slot holds the hi and lo tiles adjacently)
-      const uint32_t idesc = tc::make_idesc_f16(128, 128), idesc2 = tc::make_idesc_f16(128, 256);
+      const uint32_t idesc = tc::make_idesc_f16(PAIR ? 256 : 128, 128), idesc2 = tc::make_idesc_f16(PAIR ? 256 : 128, 256);
       uint32_t it = 0, px = 0;
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
         for (int l = 0; l < nl; ++l) {
           const int halves = (l == nl - 1) ? 1 : 2;
-          tc::mbar_wait(x_full, px);
+          if (PAIR) tc::mbar_wait_cluster(x_full, px);
+          else tc::mbar_wait(x_full, px);
           px ^= 1;
           tc::tc_fence_after();
           for (int c = 0; c < 8; ++c) {
@@ -1659,19 +1704,32 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
             for (int hf = 0; hf < halves; ++hf, ++it) {
               const uint32_t slot = it % FTC_RING;
               tc::mbar_wait(&w_full[slot], (it / FTC_RING) & 1);
+              if (PAIR) tc::mbar_wait_cluster(&w_peer[slot], (it / FTC_RING) & 1);
               tc::tc_fence_after();
-              const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
+              const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT));
               const uint32_t d_main = tmem_base + (uint32_t)hf * 256u, d_corr = d_main + 128u;
+              if (PAIR) {
+                const uint64_t bx = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT + 8192));   // this CTA's 64 rows of w_hi
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                tc::umma_f16(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
-                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, 1);
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);
+                  tc::umma_f16_pair(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
+                  tc::umma_f16_pair(d_corr, al + adv, bx + adv, idesc, 1);
+                }
+                tc::umma_commit_pair(&w_empty[slot], 3);
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  const uint64_t adv = (uint64_t)(ks * 2);
+                  tc::umma_f16(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
+                  tc::umma_f16(d_corr, al + adv, bh + adv, idesc, 1);
+                }
+                tc::umma_commit(&w_empty[slot]);
               }
-              tc::umma_commit(&w_empty[slot]);
             }
           }
-          tc::umma_commit(d_full);
+          if (PAIR) tc::umma_commit_pair(d_full, 3);
+          else tc::umma_commit(d_full);
         }
     }
   } else {
@@ -1685,7 +1743,7 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     float* Z = reinterpret_cast<float*>(xs);
     uint32_t pd = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile_first; tile < tile_end; tile += tile_step) {
       const int64_t a0 = tile * 128;
       const int rows = (int)min((int64_t)128, p.n_atoms - a0);
       // ---- stage the node tile: warp `we` loads rows we, we+16, ... (1 KB coalesced per row),
@@ -1729,7 +1787,10 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
       }
       tc::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(x_full);
+      if (lane == 0) {
+        if (PAIR) tc::mbar_arrive_cluster(x_full_ldr);
+        else tc::mbar_arrive(x_full);
+      }
 
       // ---- residual layers: thread = (row, 64 columns = K-chunks 2cq, 2cq+1 of the next layer's operand)
       for (int l = 0; l + 1 < nl; ++l) {
@@ -1776,7 +1837,10 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
         tc::fence_proxy_async();
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(x_full);
+        if (lane == 0) {
+          if (PAIR) tc::mbar_arrive_cluster(x_full_ldr);
+          else tc::mbar_arrive(x_full);
+        }
       }
       // ---- last layer: Z = act(D + b), 128 columns; each (row, quarter) thread takes 32 of them
       {
@@ -1865,8 +1929,21 @@ __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcT
     }
   }
   tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+  if (PAIR) tc::cluster_sync();
+  else __syncthreads();
+  if (warp == 1) {
+    if (PAIR) tc::tmem_dealloc_pair<512>(tmem_base);
+    else tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcTcArgs p) {
+  fc_readout_tc_body<ACT, false>(p);
+}
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FTC_THREADS, 1) fc_readout_pair_kernel(const FcTcArgs p) {
+  fc_readout_tc_body<ACT, true>(p);
 }
 
 }  // namespace nmr

@@ -362,35 +362,35 @@ def test_config2_full_size_properties(model, config2_batch):
     assert np.array_equal(ShardedModel(model)(config2_batch), y_tc)
 
 
-def test_mp_layer_cta_pair_form_is_bit_identical(config2_batch):
-    """Option "mp_pair": the MP layers as CTA pairs (cta_group::2, M = 256 per instruction, each CTA staging half of
-    W').  Same products in the same order, so the peaks must equal the one-CTA kernel's bit for bit — for an even
-    and an odd number of 128-atom tiles (the odd one leaves the peer CTA of the last pair with an empty tile)."""
+def test_cta_pair_kernels_are_bit_identical(config2_batch):
+    """Options "mp_pair" / "fc_pair": the MP layers and the node MLP as CTA pairs (cta_group::2, M = 256 per
+    instruction, the B operand split between the two CTAs).  Same products in the same order, so the peaks must equal
+    the one-CTA kernels' bit for bit — for even and odd numbers of 128-atom tiles (an odd count leaves the peer CTA
+    of the last pair with an empty tile)."""
     import nmrgnn_b200
     from nmrgnn_b200.workloads import take_graphs
     m = nmrgnn_b200.load_model()
+
+    def run(g, mp_pair, fc_pair):
+        m.handle.set_option("mp_pair", mp_pair)
+        m.handle.set_option("fc_pair", fc_pair)
+        return m(g)
+
     try:
         m.handle.set_option("tc_min_atoms", 0)
-        offs = config2_batch[4]
-        cases = [take_graphs(config2_batch, np.array([0])), take_graphs(config2_batch, np.array([1, 2, 3])), config2_batch]
-        parities = set()
-        for g in cases:
-            n = g[0].shape[0]
-            parities.add(((n + 127) // 128) & 1)
-            m.handle.set_option("mp_pair", 0)
-            y0 = m(g[:4])
-            m.handle.set_option("mp_pair", 1)
-            y1 = m(g[:4])
-            assert m.handle.compute_path.startswith("tcgen05")
-            assert np.array_equal(y0, y1), n
+        assert m.handle.compute_path.startswith("tcgen05")
+        cases = [take_graphs(config2_batch, np.array([0]))[:4], take_graphs(config2_batch, np.array([1, 2, 3]))[:4],
+                 config2_batch[:4]]
         # a graph cut to an odd / even number of tiles so that both parities are always covered
         for n in (128 * 9 + 5, 128 * 10):
             a, nl, e, inv = (x[:n] for x in config2_batch[:4])
-            nl = np.where(nl < n, nl, 0).astype(nl.dtype)
-            m.handle.set_option("mp_pair", 0)
-            y0 = m((a, nl, e, inv))
-            m.handle.set_option("mp_pair", 1)
-            assert np.array_equal(m((a, nl, e, inv)), y0), n
+            cases.append((a, np.where(nl < n, nl, 0).astype(nl.dtype), e, inv))
+        for g in cases:
+            n = g[0].shape[0]
+            y0 = run(g, 0, 0)
+            assert np.array_equal(run(g, 1, 0), y0), ("mp_pair", n)
+            assert np.array_equal(run(g, 0, 1), y0), ("fc_pair", n)
+            assert np.array_equal(run(g, 1, 1), y0), ("both", n)
     finally:
         m.close()
 
