@@ -36,6 +36,21 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert lib.nmrgnn_abi_version() == 1
 
 
+def test_every_runtime_option_is_documented_in_the_header():
+    """nmrgnn_set_option: every name the library accepts is described in include/nmrgnn_b200.h (and nothing else is)."""
+    with open(os.path.join(ROOT, "nmrgnn_b200", "csrc", "api.cu")) as f:
+        src = f.read()
+    body = src[src.index("int nmrgnn_set_option("):]
+    body = body[:body.index("\n}\n")]
+    accepted = set(re.findall(r'std::strcmp\(name, "([a-z0-9_]+)"\)', body))
+    assert {"profile", "force_ffma", "tc_min_atoms", "mp_pair", "fc_pair"} <= accepted
+    with open(os.path.join(ROOT, "include", "nmrgnn_b200.h")) as f:
+        header = f.read()
+    doc = header[header.index("Runtime options"):header.index("int nmrgnn_set_option(")]
+    documented = set(re.findall(r'"([a-z0-9_]+)"', doc))
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
+
+
 def test_num_weights_and_null_handling(lib_path):
     from nmrgnn_b200 import _capi
     lib = _capi.load_library()
