@@ -163,6 +163,9 @@ int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap);
  *   "mp_pair" = 1: MP layers as CTA pairs (cta_group::2: one M = 256 instruction stream per two neighbouring
  *                  128-atom tiles, each CTA staging half of W'; bit-identical output; measured 5 % slower than the
  *                  one-CTA form on B200, kept as the base of the next round's work);
+ *   "edge_split" = 1: edge MLP with its 16 epilogue warps split into two groups of 8, one per tile slot (the default
+ *                  has all 16 work on one slot at a time); bit-identical output; environment NMRGNN_EDGE_SPLIT=1
+ *                  selects it for every handle of the process;
  *   "fc_pair" = 1: node MLP as CTA pairs (cta_group::2; the merged [w_hi | w_lo] operand splits into w_hi on the
  *                  leader and w_lo on the peer; bit-identical output; measured slower, 0.50 vs 0.40 ms, kept as the
  *                  base of the next round's work);

@@ -415,8 +415,13 @@ static_assert(true, "");
 constexpr size_t ETC_SMEM = 1024 + 2 * ETC_X_BYTES + ETC_RING * 16384 + 128 * 16 + 2 * 4 * 128 * 16 +
                             (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
 
-template <int ACT>
-__global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeTcArgs p) {
+// SPLIT (option "edge_split"): the 16 epilogue warps form two groups of 8, one per slot, instead of all working on
+// slot 0, then slot 1.  With every warp in the same phase at the same time the MUFU pipe (2 per element, 16 per
+// clock and SM: 2.05 k cycles per tile and layer, the floor of this kernel) idles while all of them load
+// accumulators or split / store operands; two groups half a period apart fill those gaps with each other's
+// softplus.  Thread = (edge row, 64 features); same arithmetic in the same order (bit-identical output).
+template <int ACT, bool SPLIT>
+__device__ __forceinline__ void edge_mlp_tc_body(const EdgeTcArgs& p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xs = smem;                                     // [2 slots][4 chunks][hi 8192 | lo 8192]
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
       tc::mbar_init(&w_empty[i], 1);
     }
     for (int g = 0; g < 2; ++g) {
-      tc::mbar_init(&x_full[g], 16);
+      tc::mbar_init(&x_full[g], SPLIT ? 8 : 16);
       tc::mbar_init(&d_full[g], 1);
     }
     tc::mbar_init(wf_full, 1);
@@ -527,6 +532,136 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
         o[0] = clock64() - k0;   // MMA thread total
         o[1] = w_x;              //   waiting for the epilogue warps (x_full)
         o[2] = w_w;              //   waiting for W (w_full)
+      }
+    }
+  } else if (SPLIT) {
+    // ===================== epilogue warps, one group of 8 per slot: thread = (edge row, 64 features) =====================
+    const int we = warp - 2;                 // 0..15
+    const int g = we >> 3;                   // this group's slot; its tiles are n = g, g + 2, g + 4, ...
+    const int q = warp & 3;                  // TMEM lane quarter (fixed by the hardware: warp % 4)
+    const int ch = (we & 7) >> 2;            // column half: K-chunks 2 ch and 2 ch + 1
+    const int row = q * 32 + lane;
+    const uint32_t xs_a = tc::smem_u32(xs) + (uint32_t)g * ETC_X_BYTES;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+    uint32_t pd = 0;
+    for (int tn = g; tn < n_my; tn += 2) {
+      // ---- RBF expansion * mask (layers.py:137-140, model.py:251-257) -> operand X of this slot
+      const int64_t tile = blockIdx.x + (int64_t)tn * gridDim.x;
+      const int64_t e = tile * 128 + row;
+      float d = 0.0f;
+      int32_t idx = 0;
+      if (e < p.n_edges) {
+        d = __ldg(p.edges + e);
+        if (p.nlist != nullptr && ch == 0) {
+          idx = __ldg(p.nlist + e);
+          if (idx < 0 || idx >= p.n_atoms) {
+            atomicOr(p.err_flag, 1);
+            idx = 0;
+          }
+        }
+      }
+      {
+        const bool m = d > 0.0f;
+        const float s_in = m ? p.in_scale[0] : 0.0f;
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int cq = ch * 2 + c2, col0 = cq * 32;
+          const uint32_t xg = xs_a + (uint32_t)cq * 16384u;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float diff = d - cen_s[col0 + j * 8 + i];
+              x[i] = tc::ex2_approx(diff * diff * p.rbf_c) * s_in;
+            }
+            uint4 hi, lo;
+            tc::split8_f16(x, hi, lo);
+            const uint32_t off = xg + tc::sw64_chunk_offset(row, j);
+            tc::sts128(off, hi);
+            tc::sts128(off + 8192u, lo);
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_full[g]);
+      }
+      for (int l = 0; l < n_hidden; ++l) {
+        const bool last = l == n_hidden - 1;
+        const float s_out = p.out_scale[l], s_in = p.in_scale[l + 1];
+        const long long q0 = p.dbg ? clock64() : 0;
+        tc::mbar_wait(&d_full[g], pd);
+        if (p.dbg && warp == 2 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 3), (unsigned long long)(clock64() - q0));
+        pd ^= 1;
+        tc::tc_fence_after();
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int cq = ch * 2 + c2, col0 = cq * 32;
+          const uint32_t bl_a = tc::smem_u32(bias_s + l * 128 + col0);
+          const uint32_t wf_a = tc::smem_u32(wf4 + col0);
+          const uint32_t t_main = t_lane + col0, t_corr = t_main + 128u;
+          const uint32_t xg = xs_a + (uint32_t)cq * 16384u;
+          float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f, o3 = 0.0f;
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            float v[16];
+            tc::tmem_ld16_combined(t_main + cc * 16, t_corr + cc * 16, v);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const float4 b0 = tc::lds128(bl_a + cc * 64 + hh * 32), b1 = tc::lds128(bl_a + cc * 64 + hh * 32 + 16);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float x[8];
+              if (!last) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  x[i] = act_t<ACT>(fmaf(v[hh * 8 + i], s_out, bb[i])) * s_in;
+                uint4 hi, lo;
+                tc::split8_f16(x, hi, lo);
+                const uint32_t off = xg + tc::sw64_chunk_offset(row, cc * 2 + hh);
+                tc::sts128(off, hi);
+                tc::sts128(off + 8192u, lo);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float y = act_t<ACT>(fmaf(v[hh * 8 + i], s_out, bb[i]));
+                  const float4 w = tc::lds128(wf_a + (uint32_t)(cc * 16 + hh * 8 + i) * 16u);
+                  o0 = fmaf(y, w.x, o0);
+                  o1 = fmaf(y, w.y, o1);
+                  o2 = fmaf(y, w.z, o2);
+                  o3 = fmaf(y, w.w, o3);
+                }
+              }
+            }
+          }
+          if (last) part[(g * 4 + cq) * 128 + row] = make_float4(o0, o1, o2, o3);
+        }
+        if (!last) {
+          tc::fence_proxy_async();
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&x_full[g]);
+        } else {
+          // final linear layer * mask (model.py:128,261): sum the four column quarters in the same fixed order
+          tc::tc_fence_before();
+          if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (ch == 0 && e < p.n_edges) {
+            const float4 p0 = part[(g * 4 + 0) * 128 + row], p1 = part[(g * 4 + 1) * 128 + row];
+            const float4 p2 = part[(g * 4 + 2) * 128 + row], p3 = part[(g * 4 + 3) * 128 + row];
+            const bool m = d > 0.0f;
+            float o[4];
+            o[0] = m ? ((p0.x + p1.x) + (p2.x + p3.x)) + bf_s[0] : 0.0f;
+            o[1] = m ? ((p0.y + p1.y) + (p2.y + p3.y)) + bf_s[1] : 0.0f;
+            o[2] = m ? ((p0.z + p1.z) + (p2.z + p3.z)) + bf_s[2] : 0.0f;
+            o[3] = m ? ((p0.w + p1.w) + (p2.w + p3.w)) + bf_s[3] : 0.0f;
+            if (p.out != nullptr)
+              for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
+            if (p.rec != nullptr) {
+              const int64_t er = p.rec_k ? rec_slot(p.rec_e0 + e, p.rec_k) - p.rec_e0 : e;
+              p.rec[er] = make_float4(o[0], o[1], o[2], __int_as_float(idx));
+            }
+          }
+        }
       }
     }
   } else {
@@ -681,6 +816,15 @@ __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeT
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeTcArgs p) {
+  edge_mlp_tc_body<ACT, false>(p);
+}
+template <int ACT>
+__global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_split_kernel(const EdgeTcArgs p) {
+  edge_mlp_tc_body<ACT, true>(p);
 }
 
 
