@@ -367,8 +367,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 //   warps 2..17  : epilogue; all 16 warps work on slot 0, then slot 1, then slot 0 ... :
 //                  warp%4 selects the TMEM lane quarter (32 edges), (warp-2)/4 the 32-column
 //                  K-chunk: thread = (edge row, 32 features).
-// The last (linear, 128 -> E) layer is one more MMA with N = 16 (E padded) against the
-// resident final-layer weights.
+// The last (linear, 128 -> E, E <= 3) layer is not a tensor-core layer (it would be 16 near-empty
+// instructions of ~105 cycles per tile): the epilogue of the last hidden layer forms its partial dot
+// products from registers in FP32 and the four column quarters meet in shared memory.  (The TS-form
+// kernel below still runs it as an N = 16 MMA against the resident final-layer image.)
 // ----------------------------------------------------------------------------------
 struct EdgeTcArgs {
   const float* edges;        // [n_edges]
@@ -411,7 +413,6 @@ constexpr int ETC_THREADS = 576;
 constexpr int ETC_RING = 4;
 constexpr int ETC_CHUNKS = 4;          // 128 / 32
 constexpr int ETC_X_BYTES = ETC_CHUNKS * 16384;
-static_assert(true, "");
 constexpr size_t ETC_SMEM = 1024 + 2 * ETC_X_BYTES + ETC_RING * 16384 + 128 * 16 + 2 * 4 * 128 * 16 +
                             (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
 
