@@ -153,19 +153,24 @@ int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float
  * cores) or a negative status. */
 int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap);
 
+/* The edge block RBFExpansion -> mask -> EdgeFCBlock -> mask (model.py:251-261) is a function of one scalar per edge.
+ * nmrgnn_create tabulates it once per model in FP64 (nodes every 2^-13 nm up to the distance where every RBF has
+ * underflowed, cubic through four nodes per interval, argument reduction exact in fp32) and checks the interpolation
+ * error at every interval midpoint; smooth activations only (softplus / tanh / linear).  Returns 1 if the table was
+ * accepted (interpolation error <= 2^-27 of the feature scale) and is used while option "edge_table" is 1, 0 if the MLP kernels
+ * evaluate every edge; *n_intervals / *rel_error (may be NULL) receive the table size and the measured error. */
+int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_error);
+
 /* Runtime options (value semantics per name):
  *   "tc_compensate" = 0: switch the compensation above off (diagnostics only; default 1);
  *   "tc_min_atoms" = n: calls with fewer than n atoms run on the exact-FP32 kernels (default 1024: a few
  *                     128-row tiles, latency-bound on either path; 0 = always use tensor cores);
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
- *   "edge_ts" = 1: edge MLP with its activation operand in tensor memory (TS-form tcgen05.mma; bit-identical
- *                  output, measured slower than the default SS form; kept for comparison);
+ *   "edge_table" = 0: evaluate the edge block (RBF -> EdgeFCBlock) with the MLP kernels (tcgen05 / FFMA) for every
+ *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
  *   "mp_pair" = 1: MP layers as CTA pairs (cta_group::2: one M = 256 instruction stream per two neighbouring
  *                  128-atom tiles, each CTA staging half of W'; bit-identical output; measured 5 % slower than the
  *                  one-CTA form on B200, kept as the base of the next round's work);
- *   "edge_split" = 1: edge MLP with its 16 epilogue warps split into two groups of 8, one per tile slot (the default
- *                  has all 16 work on one slot at a time); bit-identical output; environment NMRGNN_EDGE_SPLIT=1
- *                  selects it for every handle of the process;
  *   "fc_pair" = 1: node MLP as CTA pairs (cta_group::2; the merged [w_hi | w_lo] operand splits into w_hi on the
  *                  leader and w_lo on the peer; bit-identical output; measured slower, 0.50 vs 0.40 ms, kept as the
  *                  base of the next round's work);

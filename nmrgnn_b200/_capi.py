@@ -21,7 +21,7 @@ EXPORTS = [
     "nmrgnn_abi_version", "nmrgnn_num_weights", "nmrgnn_create", "nmrgnn_destroy", "nmrgnn_forward",
     "nmrgnn_edge_features", "nmrgnn_embed", "nmrgnn_mp_layer", "nmrgnn_fc_readout", "nmrgnn_synchronize",
     "nmrgnn_kernel_launches", "nmrgnn_compute_path", "nmrgnn_last_error", "nmrgnn_knn_graph",
-    "nmrgnn_set_option", "nmrgnn_selftest_gemm", "nmrgnn_stage_times", "nmrgnn_tc_compensation",
+    "nmrgnn_set_option", "nmrgnn_selftest_gemm", "nmrgnn_stage_times", "nmrgnn_tc_compensation", "nmrgnn_edge_table_info",
 ]
 
 
@@ -73,6 +73,7 @@ def load_library() -> C.CDLL:
     lib.nmrgnn_selftest_gemm.argtypes = [vp, fp, fp, fp, C.c_int]
     lib.nmrgnn_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.nmrgnn_tc_compensation.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    lib.nmrgnn_edge_table_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     if lib.nmrgnn_abi_version() != 1:
         raise ImportError("libnmrgnn_b200.so ABI version mismatch")
     _lib = lib
@@ -152,6 +153,15 @@ class Handle:
         if n < 0:
             self.check(n)
         return {"edge": float(buf[0]), "mp_layers": [float(buf[i]) for i in range(1, n)]}
+
+    def edge_table_info(self) -> dict:
+        """Create-time table of the edge block: {'active', 'intervals', 'rel_error'} (nmrgnn_edge_table_info)."""
+        n = C.c_int32(0)
+        err = C.c_double(0.0)
+        rc = self._lib.nmrgnn_edge_table_info(self._h, C.byref(n), C.byref(err))
+        if rc < 0:
+            self.check(rc)
+        return {"active": bool(rc), "intervals": int(n.value), "rel_error": float(err.value)}
 
     def synchronize(self, stream: Optional[int] = None) -> None:
         self.check(self._lib.nmrgnn_synchronize(self._h, stream))

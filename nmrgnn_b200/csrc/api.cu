@@ -18,6 +18,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_tc.cuh"
 #include "knn.cuh"
+#include "edge_table.cuh"
 
 using namespace nmr;
 
@@ -84,12 +85,17 @@ struct nmrgnn_handle {
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
   bool compensate = true;
-  bool edge_split = false;              // option "edge_split": edge-MLP epilogue as two groups of 8 warps, one per slot
   bool fc_pair = false;                 // option "fc_pair": the CTA-pair (cta_group::2) form of the node-MLP kernel
   bool mp_pair = false;                 // option "mp_pair": the CTA-pair (cta_group::2) form of the MP-layer kernel
-  bool edge_ts = false;                 // option "edge_ts": the TS-form edge kernel (activation operand in tensor memory)
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
+  // edge block as a create-time FP64 table of the scalar function d -> EdgeFC(RBF(d)) (edge_table.cuh)
+  bool edge_table = true;               // option "edge_table"
+  bool edge_tab_ok = false;             // table built and its interpolation error accepted
+  const float4* edge_tab = nullptr;     // [edge_tab_n][E] cubic coefficients
+  int edge_tab_n = 0;
+  float edge_tab_finf[EDGE_TAB_MAX_E] = {0.f, 0.f, 0.f, 0.f};
+  double edge_tab_err = 0.0;            // max interpolation error at interval midpoints / feature scale
 };
 
 namespace {
@@ -299,6 +305,23 @@ int end_call(nmrgnn_handle* h, void* stream, cudaStream_t s) {
   return nmrgnn_synchronize(h, nullptr);
 }
 
+// name of the compute path a full-size call takes with the current options (nmrgnn_compute_path)
+void update_path(nmrgnn_handle* h) {
+  const bool table = h->edge_table && h->edge_tab_ok;
+  std::string p;
+  if (!h->fast_path) p = "generic-fp32";
+  else if (!h->tc_ok || h->force_ffma) p = "ffma";
+  else {
+    std::string blocks = table ? "" : "edge";
+    if (h->mp_tc_ok) blocks += blocks.empty() ? "mp" : ",mp";
+    if (h->fc_tc_ok) blocks += blocks.empty() ? "fc" : ",fc";
+    p = "tcgen05-fp16x3(" + blocks + ")";
+    if (!h->mp_tc_ok || !h->fc_tc_ok) p += "+ffma";
+  }
+  if (table) p = "edge-table-f64+" + p;
+  h->path = p;
+}
+
 int grid_for(const nmrgnn_handle* h, int64_t tiles, int per_sm) {
   int64_t g = (int64_t)h->num_sms * per_sm;
   return (int)(tiles < g ? (tiles < 1 ? 1 : tiles) : g);
@@ -354,11 +377,99 @@ int launch_edge_generic(nmrgnn_handle* h, cudaStream_t s, const float* edges, in
   return NMRGNN_OK;
 }
 
+// ---------------------------------------------------------------------------- edge table (edge_table.cuh)
+// Tabulates d -> EdgeFC(RBF(d)) in FP64 on the device, derives the per-interval cubics and accepts the table if the
+// interpolation error measured at every interval midpoint stays below 2^-27 of the feature scale.
+int build_edge_table(nmrgnn_handle* h) {
+  const int H = h->d.edge_hidden, E = h->d.edge_features, act = h->d.fc_activation;
+  h->edge_tab_ok = false;
+  if (H > 256 || E > EDGE_TAB_MAX_E || act == ACT_RELU) return NMRGNN_OK;   // relu: f has kinks, a cubic does not follow them
+  if (!(h->gap > 0.f)) return NMRGNN_OK;
+  // beyond d_max every RBF has underflowed to zero in float32 (exp(-104) < 2^-149): f is the constant EdgeFC(0)
+  const double d_max = (double)h->d.rbf_high + std::sqrt(104.0 * (double)h->gap);
+  const double n_d = std::ceil(d_max * (double)EDGE_TAB_INV_H) + 1.0;
+  if (!(n_d >= 1.0) || n_d > 1048576.0) return NMRGNN_OK;
+  const int n = (int)n_d, n_nodes = n + 4;
+  double *nodes = nullptr, *mids = nullptr, *err = nullptr;
+  float4* tab = nullptr;
+  auto cleanup = [&]() {
+    if (nodes) cudaFree(nodes);
+    if (mids) cudaFree(mids);
+    if (err) cudaFree(err);
+  };
+  cudaStream_t s = h->stream;
+  if (cudaMalloc(&nodes, (size_t)n_nodes * E * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&mids, (size_t)n_nodes * E * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&err, 2 * EDGE_TAB_MAX_E * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&tab, (size_t)n * E * sizeof(float4) + 16) != cudaSuccess) {
+    cleanup();
+    if (tab) cudaFree(tab);
+    return fail(h, NMRGNN_ERR_OOM, "edge table allocation failed");
+  }
+  h->owned.push_back((float*)tab);
+  EdgeTabBuildArgs a{};
+  for (int i = 0; i < h->d.n_edge_fc; ++i) {
+    a.W[i] = h->edge_W[i];
+    a.b[i] = h->edge_b[i];
+  }
+  a.centers = h->centers;
+  a.gap = h->gap;
+  a.n_layers = h->d.n_edge_fc;
+  a.H = H;
+  a.E = E;
+  a.act = act;
+  a.n_nodes = n_nodes;
+  a.nodes = nodes;
+  a.mids = mids;
+  cudaMemsetAsync(err, 0, 2 * EDGE_TAB_MAX_E * sizeof(double), s);
+  edge_table_nodes_kernel<<<2 * n_nodes, 256, 0, s>>>(a);
+  edge_table_coef_kernel<<<(n + 127) / 128, 128, 0, s>>>(nodes, mids, n, E, tab, err);
+  double herr[2 * EDGE_TAB_MAX_E];
+  std::vector<double> finf(E);
+  cudaError_t e1 = cudaMemcpyAsync(herr, err, sizeof(herr), cudaMemcpyDeviceToHost, s);
+  cudaError_t e2 = cudaMemcpyAsync(finf.data(), nodes + (size_t)(n_nodes - 1) * E, E * sizeof(double), cudaMemcpyDeviceToHost, s);
+  cudaError_t e3 = cudaStreamSynchronize(s);
+  cleanup();
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || cudaGetLastError() != cudaSuccess)
+    return fail(h, NMRGNN_ERR_CUDA, "edge table build failed: %s", cudaGetErrorString(e3 != cudaSuccess ? e3 : e1));
+  double rel = 0.0;
+  for (int c = 0; c < E; ++c) rel = std::max(rel, herr[EDGE_TAB_MAX_E + c] > 0.0 ? herr[c] / herr[EDGE_TAB_MAX_E + c] : 0.0);
+  h->edge_tab_err = rel;
+  for (int c = 0; c < E; ++c) h->edge_tab_finf[c] = (float)finf[c];
+  h->edge_tab = tab;
+  h->edge_tab_n = n;
+  h->edge_tab_ok = std::isfinite(rel) && rel <= 1.0 / 134217728.0;   // 2^-27
+  return NMRGNN_OK;
+}
+
 bool rec_swizzled(int K) { return K == 8 || K == 16; }
+
+int launch_edge_table(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out, const int32_t* nlist,
+                      int64_t n_atoms, float4* rec, int K, int64_t e0) {
+  EdgeTabArgs t{};
+  t.edges = edges;
+  t.nlist = nlist;
+  t.out = out;
+  t.rec = rec;
+  t.n_edges = n_edges;
+  t.n_atoms = n_atoms;
+  t.tab = h->edge_tab;
+  t.n_intervals = h->edge_tab_n;
+  for (int c = 0; c < EDGE_TAB_MAX_E; ++c) t.f_inf[c] = h->edge_tab_finf[c];
+  t.E = h->d.edge_features;
+  t.err_flag = h->err_flag;
+  t.rec_k = (rec != nullptr && rec_swizzled(K)) ? K : 0;
+  t.rec_e0 = e0;
+  edge_table_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, s>>>(t);
+  h->launches++;
+  return NMRGNN_OK;
+}
 
 int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_edges, float* out,
                 const int32_t* nlist, int64_t n_atoms, float4* rec = nullptr, int K = 0, int64_t e0 = 0) {
   if (n_edges == 0) return NMRGNN_OK;
+  if (h->edge_table && h->edge_tab_ok && (rec == nullptr || h->d.edge_features <= 3))
+    return launch_edge_table(h, s, edges, n_edges, out, nlist, n_atoms, rec, K, e0);
   if (!h->fast_path) return launch_edge_generic(h, s, edges, n_edges, out, nlist, n_atoms);
   if (h->tc_ok && !h->force_ffma) {
     EdgeTcArgs t{};
@@ -388,9 +499,7 @@ int launch_edge(nmrgnn_handle* h, cudaStream_t s, const float* edges, int64_t n_
     t.rec_k = (rec != nullptr && rec_swizzled(K)) ? K : 0;
     t.rec_e0 = e0;
     const int64_t tiles = (n_edges + 127) / 128;
-    if (h->edge_split && !h->edge_ts) ACT_DISPATCH(t.act, edge_mlp_split_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
-    else if (!h->edge_ts) ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
-    else ACT_DISPATCH(t.act, edge_mlp_ts_kernel, grid_for(h, tiles, 1), ETS_THREADS, ETS_SMEM, s, t);
+    ACT_DISPATCH(t.act, edge_mlp_tc_kernel, grid_for(h, tiles, 1), ETC_THREADS, ETC_SMEM, s, t);
     h->launches++;
     return NMRGNN_OK;
   }
@@ -877,6 +986,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     rbf_grid(dims->rbf_low, dims->rbf_high, H, c, h->gap);
     TRY_RC(upload(h, c.data(), c.size(), &h->centers));
   }
+  TRY_RC(build_edge_table(h));
 
   h->fast_path = (F == 256 && H == 128 && E >= 1 && E <= 4);
   if (h->fast_path) {
@@ -921,11 +1031,6 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(upload_bytes(h, img.data(), img.size(), &h->edge_f_img));
     TRY_RC(upload(h, bias.data(), bias.size(), &h->edge_bias));
     ACT_SET_SMEM(edge_mlp_tc_kernel, ETC_SMEM);
-    ACT_SET_SMEM(edge_mlp_split_kernel, ETC_SMEM);
-    // diagnostics: NMRGNN_EDGE_SPLIT=1 in the environment selects the "edge_split" form for every handle of the
-    // process (lets the whole test-suite run on it without touching the tests)
-    if (const char* ev = std::getenv("NMRGNN_EDGE_SPLIT")) h->edge_split = ev[0] == '1';
-    ACT_SET_SMEM(edge_mlp_ts_kernel, ETS_SMEM);
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STH_SMEM));
     CUDA_RC(cudaFuncSetAttribute(tc_selftest_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STH_SMEM));
@@ -1007,14 +1112,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
     ACT_SET_SMEM(fc_readout_pair_kernel, FTC_SMEM);
   }
-  h->path = h->fast_path ? "ffma" : "generic-fp32";
-  if (h->tc_ok) {
-    h->path = "tcgen05-fp16x3(edge";
-    if (h->mp_tc_ok) h->path += ",mp";
-    if (h->fc_tc_ok) h->path += ",fc";
-    h->path += ")";
-    if (!h->mp_tc_ok || !h->fc_tc_ok) h->path += "+ffma";
-  }
+  update_path(h);
 #undef TRY_RC
 #undef CUDA_RC
   *out = h;
@@ -1297,6 +1395,13 @@ int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap) {
   return n + 1;
 }
 
+int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_error) {
+  if (!h) return NMRGNN_ERR_BAD_DIMS;
+  if (n_intervals) *n_intervals = h->edge_tab_n;
+  if (rel_error) *rel_error = h->edge_tab_err;
+  return h->edge_tab_ok ? 1 : 0;
+}
+
 int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   if (!h || !name) return NMRGNN_ERR_BAD_DIMS;
   if (std::strcmp(name, "profile") == 0) {
@@ -1306,6 +1411,7 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "force_ffma") == 0) {
     h->force_ffma = value != 0;
+    update_path(h);
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_role_counters") == 0) {
@@ -1333,10 +1439,6 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
     if (value == 0) h->mp_dbg = nullptr;
     return NMRGNN_OK;
   }
-  if (std::strcmp(name, "edge_split") == 0) {
-    h->edge_split = value != 0;
-    return NMRGNN_OK;
-  }
   if (std::strcmp(name, "fc_pair") == 0) {
     h->fc_pair = value != 0;
     return NMRGNN_OK;
@@ -1345,8 +1447,9 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
     h->mp_pair = value != 0;
     return NMRGNN_OK;
   }
-  if (std::strcmp(name, "edge_ts") == 0) {
-    h->edge_ts = value != 0;
+  if (std::strcmp(name, "edge_table") == 0) {
+    h->edge_table = value != 0;
+    update_path(h);
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "tc_min_atoms") == 0) {

@@ -7,17 +7,29 @@ namespace nmr {
 
 enum : int { ACT_LINEAR = 0, ACT_SOFTPLUS = 1, ACT_RELU = 2, ACT_TANH = 3 };
 
-// softplus(x) = max(x,0) + log(1 + exp(-|x|)).  The reference's TF kernel computes
-// log(exp(x) + 1) with thresholds (tensorflow/core/kernels/softplus_op.h); both
-// forms carry an absolute error of ~eps/2 from rounding 1+t, so the MUFU-based
-// ex2/lg2 evaluation below (2 MUFU + 4 FP32 ops) stays inside that envelope.
-// (ex2.approx.ftz / lg2.approx directly: __expf() adds a compare and two predicated multiplies per call to keep
-//  results below 2^-126 denormal-exact, which log(1 + t) cannot see)
+// softplus(x) = max(x,0) + log1p(t), t = exp(-|x|) in (0, 1].
+// t comes from MUFU ex2 (relative error 2^-22, harmless); log1p(t) = t * P9(t) is a degree-9 near-minimax polynomial
+// for log1p(t)/t on [0, 1] (approximation error 4.8e-9, measured relative error of the fp32 evaluation <= 1.7e-7, mean
+// 1e-8).  The obvious MUFU form lg2.approx(1 + t) is NOT good enough here: near 1 lg2.approx carries an absolute error
+// of ~2^-23 with a constant positive offset (+1.2 x 2^-24 measured on B200, tools/microbench/softplus_err.cu), i.e. every
+// small activation (x < -2) came out too large by the same 7e-8 -- up to 100 % of its value -- and the next layer sums
+// that offset coherently over hundreds of inputs; that bias was the largest single contribution to the peak error of
+// both compute paths (profiles/r02_softplus_bias.md).  The reference's TF kernel computes log(exp(x) + 1) with
+// thresholds (tensorflow/core/kernels/softplus_op.h); this form is closer to the exact function than that one.
 __device__ __forceinline__ float softplus_f(float x) {
-  float t, l;
+  float t;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-1.4426950408889634f * fabsf(x)));
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
-  return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.0f));
+  float p = -3.256378463e-03f;
+  p = fmaf(p, t, 1.990716159e-02f);
+  p = fmaf(p, t, -5.706420168e-02f);
+  p = fmaf(p, t, 1.061426476e-01f);
+  p = fmaf(p, t, -1.531186253e-01f);
+  p = fmaf(p, t, 1.967811733e-01f);
+  p = fmaf(p, t, -2.495455891e-01f);
+  p = fmaf(p, t, 3.333000541e-01f);
+  p = fmaf(p, t, -4.999990463e-01f);
+  p = fmaf(p, t, 1.0f);
+  return fmaf(p, t, fmaxf(x, 0.0f));
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {

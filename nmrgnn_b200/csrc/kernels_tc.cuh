@@ -823,291 +823,6 @@ template <int ACT>
 __global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_tc_kernel(const EdgeTcArgs p) {
   edge_mlp_tc_body<ACT, false>(p);
 }
-template <int ACT>
-__global__ void __launch_bounds__(ETC_THREADS, 1) edge_mlp_split_kernel(const EdgeTcArgs p) {
-  edge_mlp_tc_body<ACT, true>(p);
-}
-
-
-// ----------------------------------------------------------------------------------
-// Edge MLP, TS form: the activation operand X lives in TENSOR memory (A operand of tcgen05.mma read from
-// TMEM), only the weights come from shared memory.  Why: an SS-mode M=128, N=128 MMA reads A (4 KB) + B (4 KB)
-// from shared memory in 64 cycles -- the SM's entire 128 B/clk shared-memory bandwidth -- so the SS kernel
-// above ran at 161 cycles per MMA while its epilogue stored the next operand into the same memory.  Here the
-// epilogue writes X with tcgen05.st (thread = edge row, packed fp16 pairs: no swizzle, no shared-memory
-// traffic) and the MMA needs 64 B/clk.
-// Tensor-memory plan (512 columns): one accumulator region shared by BOTH tiles in flight
-//   [0,128) main  [128,256) corr      [256,320) X0 hi  [320,384) X0 lo      [384,448) X1 hi  [448,512) X1 lo
-// The epilogue warps first pull a tile's accumulators into registers and release the region (acc_free); the
-// MMAs of the other tile then run while the CUDA cores turn those registers into the next operand.
-//   warp 0: W loader (16 KB bulk copies, 8-slot ring)   warp 1: MMA issuer + TMEM owner
-//   warps 2..17: epilogue, thread = (edge row, 32 features); all 16 warps serve slot 0, slot 1, slot 0, ...
-// ----------------------------------------------------------------------------------
-constexpr int ETS_THREADS = 576;
-constexpr int ETS_RING = 8;
-constexpr size_t ETS_SMEM = 1024 + ETS_RING * 16384 + ETC_CHUNKS * 2048 + (MAX_DENSE * 128 + 128 + 16) * 4 + 512;
-
-template <int ACT>
-__global__ void __launch_bounds__(ETS_THREADS, 1) edge_mlp_ts_kernel(const EdgeTcArgs p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;                                   // [RING][hi 8192 | lo 8192]
-  uint8_t* wf = ring + ETS_RING * 16384;                  // [4][hi 1024 | lo 1024]
-  float* bias_s = reinterpret_cast<float*>(wf + ETC_CHUNKS * 2048);   // [n_hidden][128]
-  float* cen_s = bias_s + MAX_DENSE * 128;                // [128]
-  float* bf_s = cen_s + 128;                              // [16]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bf_s + 16);
-  uint64_t* w_full = bars;                                // [RING]
-  uint64_t* w_empty = w_full + ETS_RING;                  // [RING]
-  uint64_t* x_full = w_empty + ETS_RING;                  // [2]
-  uint64_t* d_full = x_full + 2;                          // [2]
-  uint64_t* acc_free = d_full + 2;
-  uint64_t* wf_full = acc_free + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wf_full + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
-    for (int i = 0; i < ETS_RING; ++i) {
-      tc::mbar_init(&w_full[i], 1);
-      tc::mbar_init(&w_empty[i], 1);
-    }
-    for (int g = 0; g < 2; ++g) {
-      tc::mbar_init(&x_full[g], 16);
-      tc::mbar_init(&d_full[g], 1);
-    }
-    tc::mbar_init(acc_free, 16);
-    tc::mbar_init(wf_full, 1);
-    tc::mbar_fence_init();
-  }
-  for (int i = tid; i < p.n_hidden * 128; i += ETS_THREADS) bias_s[i] = p.bias[i];
-  for (int i = tid; i < 128; i += ETS_THREADS) cen_s[i] = p.centers[i];
-  if (tid < 16) bf_s[tid] = tid < p.E ? p.bias_f[tid] : 0.0f;
-  if (warp == 1) tc::tmem_alloc<512>(tmem_slot);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int64_t n_tiles = (p.n_edges + 127) / 128;
-  const int n_hidden = p.n_hidden;
-  const int n_my = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-
-  if (warp == 0) {
-    // ===================== weight loader =====================
-    if (lane == 0 && n_my > 0) {
-      tc::mbar_expect_tx(wf_full, ETC_CHUNKS * 2048);
-      tc::bulk_g2s(wf, p.Wfimg, ETC_CHUNKS * 2048, wf_full);
-      uint32_t it = 0;
-      for (int pair = 0; pair * 2 < n_my; ++pair)
-        for (int l = 0; l < n_hidden; ++l)
-          for (int g = 0; g < 2; ++g) {
-            if (pair * 2 + g >= n_my) continue;
-            for (int c = 0; c < ETC_CHUNKS; ++c, ++it) {
-              const uint32_t slot = it % ETS_RING, ph = (it / ETS_RING) & 1;
-              tc::mbar_wait(&w_empty[slot], ph ^ 1);
-              tc::mbar_expect_tx(&w_full[slot], 16384);
-              tc::bulk_g2s(ring + slot * 16384, p.Wimg + ((size_t)l * ETC_CHUNKS + c) * 16384, 16384, &w_full[slot]);
-            }
-          }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0 && n_my > 0) {
-      const uint32_t idesc_h2 = tc::make_idesc_f16(128, 256), idesc_h = tc::make_idesc_f16(128, 128);
-      const uint32_t idesc_f2 = tc::make_idesc_f16(128, 32), idesc_f = tc::make_idesc_f16(128, 16);
-      const uint32_t d_main = tmem_base, d_corr = tmem_base + 128u;
-      tc::mbar_wait(wf_full, 0);
-      uint32_t it = 0, px[2] = {0, 0}, use = 0;
-      long long w_x = 0, w_w = 0, w_a = 0, c0 = 0;
-      const long long k0 = clock64();
-      for (int pair = 0; pair * 2 < n_my; ++pair)
-        for (int l = 0; l <= n_hidden; ++l)
-          for (int g = 0; g < 2; ++g) {
-            if (pair * 2 + g >= n_my) continue;
-            const bool fin = (l == n_hidden);
-            const uint32_t xa = tmem_base + 256u + (uint32_t)g * 128u;      // X_g: hi [0,64), lo [64,128)
-            if (p.dbg) c0 = clock64();
-            tc::mbar_wait(&x_full[g], px[g]);
-            if (p.dbg) w_x += clock64() - c0, c0 = clock64();
-            px[g] ^= 1;
-            tc::mbar_wait(acc_free, (use & 1) ^ 1);     // the previous user's accumulators are in registers
-            if (p.dbg) w_a += clock64() - c0;
-            ++use;
-            tc::tc_fence_after();
-            for (int c = 0; c < ETC_CHUNKS; ++c) {
-              uint64_t bh, bl;
-              uint32_t slot = 0;
-              if (!fin) {
-                slot = it % ETS_RING;
-                if (p.dbg) c0 = clock64();
-                tc::mbar_wait(&w_full[slot], (it / ETS_RING) & 1);
-                if (p.dbg) w_w += clock64() - c0;
-                tc::tc_fence_after();
-                bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384));
-                bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * 16384 + 8192));
-              } else {
-                bh = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048));
-                bl = tc::make_desc_sw64(tc::smem_u32(wf + c * 2048 + 1024));
-              }
-              (void)bl;
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                const uint32_t ah = xa + (uint32_t)(c * 2 + ks) * 8u, al = ah + 64u;
-                tc::umma_f16_ts(d_main, ah, bh + adv, fin ? idesc_f2 : idesc_h2, (c | ks) != 0);
-                tc::umma_f16_ts(fin ? d_main + 16u : d_corr, al, bh + adv, fin ? idesc_f : idesc_h, 1);
-              }
-              if (!fin) {
-                tc::umma_commit(&w_empty[slot]);
-                ++it;
-              }
-            }
-            tc::umma_commit(&d_full[g]);
-          }
-      if (p.dbg) {
-        long long* o = p.dbg + (size_t)blockIdx.x * 8;
-        o[0] = clock64() - k0;   // MMA thread total
-        o[1] = w_x;              //   waiting for the operand (x_full)
-        o[2] = w_w;              //   waiting for W (w_full)
-        o[4] = w_a;              //   waiting for the accumulator region (acc_free)
-      }
-    }
-  } else {
-    // ===================== epilogue warps: thread = (edge row, 32 features) =====================
-    const int we = warp - 2;                 // 0..15
-    const int q = warp & 3;                  // TMEM lane quarter
-    const int cq = we >> 2;                  // column quarter = K-chunk written by this thread
-    const int row = q * 32 + lane;
-    const int col0 = cq * 32;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t pd[2] = {0, 0};
-    // this thread's 32 operand values -> packed hi / lo words -> tensor memory
-    auto store_x = [&](int g, const float (&x)[32]) {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) tc::split2_f16(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
-      const uint32_t xa = t_lane + 256u + (uint32_t)g * 128u + (uint32_t)cq * 16u;
-      tc::tmem_st16(xa, hi);
-      tc::tmem_st16(xa + 64u, lo);
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&x_full[g]);
-    };
-    for (int pair = 0; pair * 2 < n_my; ++pair) {
-      const int n_in_pair = min(2, n_my - pair * 2);
-      float dd[2];
-      int32_t idxs[2] = {0, 0};
-      int64_t eidx[2];
-      // pass 0: RBF expansion * mask  (layers.py:137-140, model.py:251-257)
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g >= n_in_pair) continue;
-        const int64_t tile = blockIdx.x + (int64_t)(pair * 2 + g) * gridDim.x;
-        const int64_t e = tile * 128 + row;
-        eidx[g] = e;
-        float d = 0.0f;
-        if (e < p.n_edges) {
-          d = __ldg(p.edges + e);
-          if (p.nlist != nullptr && cq == 0) {
-            int32_t idx = __ldg(p.nlist + e);
-            if (idx < 0 || idx >= p.n_atoms) {
-              atomicOr(p.err_flag, 1);
-              idx = 0;
-            }
-            idxs[g] = idx;
-          }
-        }
-        dd[g] = d;
-        const float s_in = d > 0.0f ? p.in_scale[0] : 0.0f;
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float diff = d - cen_s[col0 + i];
-          x[i] = tc::ex2_approx(diff * diff * p.rbf_c) * s_in;   // exp(-(d - mu)^2 / gap)
-        }
-        store_x(g, x);
-      }
-      // hidden layers: X <- act(D * 2^s + b) * 2^-s'
-      for (int l = 0; l < n_hidden; ++l) {
-        const uint32_t bl_a = tc::smem_u32(bias_s + l * 128 + col0);
-        const float s_out = p.out_scale[l], s_in = p.in_scale[l + 1];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (g >= n_in_pair) continue;
-          const long long q0 = p.dbg ? clock64() : 0;
-          tc::mbar_wait(&d_full[g], pd[g]);
-          if (p.dbg && warp == 2 && lane == 0)
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 3), (unsigned long long)(clock64() - q0));
-          pd[g] ^= 1;
-          tc::tc_fence_after();
-          // accumulators -> registers, then hand the region to the other tile's MMAs
-          float x[32];
-          {
-            uint32_t a0[16], b0[16], a1[16], b1[16];
-            tc::tmem_ld16_nowait(t_lane + col0, a0);
-            tc::tmem_ld16_nowait(t_lane + 128u + col0, b0);
-            tc::tmem_ld16_nowait(t_lane + col0 + 16, a1);
-            tc::tmem_ld16_nowait(t_lane + 128u + col0 + 16, b1);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              x[i] = fmaf(__uint_as_float(b0[i]), tc::LO_UNSCALE, __uint_as_float(a0[i]));
-              x[16 + i] = fmaf(__uint_as_float(b1[i]), tc::LO_UNSCALE, __uint_as_float(a1[i]));
-            }
-          }
-          tc::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(acc_free);
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = tc::lds128(bl_a + i * 4);
-            x[i + 0] = act_t<ACT>(fmaf(x[i + 0], s_out, b4.x)) * s_in;
-            x[i + 1] = act_t<ACT>(fmaf(x[i + 1], s_out, b4.y)) * s_in;
-            x[i + 2] = act_t<ACT>(fmaf(x[i + 2], s_out, b4.z)) * s_in;
-            x[i + 3] = act_t<ACT>(fmaf(x[i + 3], s_out, b4.w)) * s_in;
-          }
-          store_x(g, x);
-        }
-      }
-      // final linear layer (columns 0..15 of the accumulators) * mask
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g >= n_in_pair) continue;
-        tc::mbar_wait(&d_full[g], pd[g]);
-        pd[g] ^= 1;
-        tc::tc_fence_after();
-        float va[8], vb[8];
-        if (cq == 0) {
-          tc::tmem_ld8(t_lane, va);
-          tc::tmem_ld8(t_lane + 16u, vb);
-        }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(acc_free);
-        if (cq == 0) {
-          const int64_t e = eidx[g];
-          if (e < p.n_edges) {
-            const bool m = dd[g] > 0.0f;
-            const float s_out = p.out_scale[n_hidden];
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o[i] = m ? fmaf(fmaf(vb[i], tc::LO_UNSCALE, va[i]), s_out, bf_s[i]) : 0.0f;
-            if (p.out != nullptr)
-              for (int i = 0; i < p.E; ++i) p.out[e * p.E + i] = o[i];
-            if (p.rec != nullptr) {
-              const int64_t er = p.rec_k ? rec_slot(p.rec_e0 + e, p.rec_k) - p.rec_e0 : e;
-              p.rec[er] = make_float4(o[0], o[1], o[2], __int_as_float(idxs[g]));
-            }
-          }
-        }
-      }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
-}
 
 }  // namespace nmr
 

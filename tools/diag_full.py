@@ -25,6 +25,7 @@ def report(name, y, ref):
 
 def main():
     m = nmrgnn_b200.load_model()
+    print("edge table:", m.handle.edge_table_info(), "| default path:", m.handle.compute_path)
     for cfg, gen in (("full_config2", lambda: workloads.protein_batch(64, first_seed=0)),
                      ("full_config3", lambda: workloads.small_molecule_batch(1024, first_seed=0))):
         z = np.load(os.path.join(ROOT, "tests", "golden", cfg + ".npz"))
