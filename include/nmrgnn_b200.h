@@ -168,12 +168,9 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "edge_table" = 0: evaluate the edge block (RBF -> EdgeFCBlock) with the MLP kernels (tcgen05 / FFMA) for every
  *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
- *   "mp_pair" = 1: MP layers as CTA pairs (cta_group::2: one M = 256 instruction stream per two neighbouring
- *                  128-atom tiles, each CTA staging half of W'; bit-identical output; measured 5 % slower than the
- *                  one-CTA form on B200, kept as the base of the next round's work);
- *   "fc_pair" = 1: node MLP as CTA pairs (cta_group::2; the merged [w_hi | w_lo] operand splits into w_hi on the
- *                  leader and w_lo on the peer; bit-identical output; measured slower, 0.50 vs 0.40 ms, kept as the
- *                  base of the next round's work);
+ *   "mp_comp_x10" = c / "mp_comp_delta_x10" = d / "fc_comp_x10" = c: diagnostics (tools/diag_comp_scan.py) -- set every MP
+ *                  layer's compensation to c / 10 x 2^-24 (negative: recalibrate), shift it by d / 10 x 2^-24, set the
+ *                  node MLP's constant;
  *   "mp_role_counters" = 1 / 2 / 0: diagnostics -- arm per-CTA cycle counters of the warp roles of the next MP-layer
  *                  or edge launch / print their means to stdout / disarm;
  *   "profile"    = 1: nmrgnn_forward records CUDA events (on the launching stream) around its

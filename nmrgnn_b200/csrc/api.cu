@@ -85,8 +85,6 @@ struct nmrgnn_handle {
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
   bool compensate = true;
-  bool fc_pair = false;                 // option "fc_pair": the CTA-pair (cta_group::2) form of the node-MLP kernel
-  bool mp_pair = false;                 // option "mp_pair": the CTA-pair (cta_group::2) form of the MP-layer kernel
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
   // edge block as a create-time FP64 table of the scalar function d -> EdgeFC(RBF(d)) (edge_table.cuh)
@@ -644,14 +642,7 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.swz = rec_swizzled(K) ? 1 : 0;
   a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
-  if (h->mp_pair) {
-    // CTA pairs: one cluster of two CTAs per pair of neighbouring tiles (cta_group::2)
-    const int64_t pairs = (tiles + 1) / 2;
-    const int clusters = (int)std::min<int64_t>(pairs, h->num_sms / 2);
-    ACT_DISPATCH(a.act, mp_layer_pair_kernel, 2 * clusters, MTC_THREADS, MTC_PAIR_SMEM, s, a);
-  } else {
-    ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
-  }
+  ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   h->launches++;
   return NMRGNN_OK;
 }
@@ -703,12 +694,7 @@ int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float*
     t.peak_std = h->peak_std;
     t.peak_avg = h->peak_avg;
     const int64_t tiles = (n + 127) / 128;
-    if (h->fc_pair) {
-      const int clusters = (int)std::min<int64_t>((tiles + 1) / 2, h->num_sms / 2);
-      ACT_DISPATCH(t.act, fc_readout_pair_kernel, 2 * clusters, FTC_THREADS, FTC_SMEM, s, t);
-    } else {
-      ACT_DISPATCH(t.act, fc_readout_tc_kernel, grid_for(h, tiles, 1), FTC_THREADS, FTC_SMEM, s, t);
-    }
+    ACT_DISPATCH(t.act, fc_readout_tc_kernel, grid_for(h, tiles, 1), FTC_THREADS, FTC_SMEM, s, t);
     h->launches++;
     return NMRGNN_OK;
   }
@@ -1062,7 +1048,6 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
-    ACT_SET_SMEM(mp_layer_pair_kernel, MTC_PAIR_SMEM);
     h->mp_corr.assign(dims->n_mp, 1.0f);
     TRY_RC(calibrate_mp(h));
     h->launches = 0;
@@ -1110,7 +1095,6 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(upload(h, bias.data(), bias.size(), &h->fc_bias));
     h->fc_rz = 1.0f + 0.17f * (float)(F / 16 + 1) / 16777216.0f;
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
-    ACT_SET_SMEM(fc_readout_pair_kernel, FTC_SMEM);
   }
   update_path(h);
 #undef TRY_RC
@@ -1439,17 +1423,22 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
     if (value == 0) h->mp_dbg = nullptr;
     return NMRGNN_OK;
   }
-  if (std::strcmp(name, "fc_pair") == 0) {
-    h->fc_pair = value != 0;
-    return NMRGNN_OK;
-  }
-  if (std::strcmp(name, "mp_pair") == 0) {
-    h->mp_pair = value != 0;
-    return NMRGNN_OK;
-  }
   if (std::strcmp(name, "edge_table") == 0) {
     h->edge_table = value != 0;
     update_path(h);
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_comp_x10") == 0) {       // diagnostics: every MP layer's compensation = value / 10 x 2^-24
+    if (value < 0) return calibrate_mp(h);               // negative: back to the calibrated constants
+    for (auto& c : h->mp_corr) c = 1.0f + (float)value / 10.0f / 16777216.0f;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_comp_delta_x10") == 0) {  // diagnostics: shift every MP layer's constant by value / 10 x 2^-24
+    for (auto& c : h->mp_corr) c += (float)value / 10.0f / 16777216.0f;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "fc_comp_x10") == 0) {        // diagnostics: node-MLP compensation = value / 10 x 2^-24
+    h->fc_rz = 1.0f + (float)value / 10.0f / 16777216.0f;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "tc_min_atoms") == 0) {

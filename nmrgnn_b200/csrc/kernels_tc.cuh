@@ -1398,10 +1398,6 @@ template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
   mp_layer_tc_body<ACT, false>(p);
 }
-template <int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MTC_THREADS, 1) mp_layer_pair_kernel(const MpTcArgs p) {
-  mp_layer_tc_body<ACT, true>(p);
-}
 
 }  // namespace nmr
 
@@ -1800,10 +1796,6 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
 template <int ACT>
 __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcTcArgs p) {
   fc_readout_tc_body<ACT, false>(p);
-}
-template <int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FTC_THREADS, 1) fc_readout_pair_kernel(const FcTcArgs p) {
-  fc_readout_tc_body<ACT, true>(p);
 }
 
 }  // namespace nmr

@@ -43,7 +43,7 @@ def test_every_runtime_option_is_documented_in_the_header():
     body = src[src.index("int nmrgnn_set_option("):]
     body = body[:body.index("\n}\n")]
     accepted = set(re.findall(r'std::strcmp\(name, "([a-z0-9_]+)"\)', body))
-    assert {"profile", "force_ffma", "tc_min_atoms", "mp_pair", "fc_pair"} <= accepted
+    assert {"profile", "force_ffma", "tc_min_atoms", "edge_table", "tc_compensate"} <= accepted
     with open(os.path.join(ROOT, "include", "nmrgnn_b200.h")) as f:
         header = f.read()
     doc = header[header.index("Runtime options"):header.index("int nmrgnn_set_option(")]

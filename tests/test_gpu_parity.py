@@ -6,7 +6,7 @@ exact zeros where the reference is exactly zero."""
 import numpy as np
 import pytest
 
-from conftest import budget_ratio, load_golden, rel_err, scaled_err, tol_ratio
+from conftest import load_golden, rel_err, scaled_err, tol_ratio
 
 pytestmark = pytest.mark.gpu
 
@@ -21,26 +21,30 @@ def model():
     m.close()
 
 
-@pytest.fixture(scope="module", params=["tc", "ffma"])
+@pytest.fixture(scope="module", params=["tc", "tc-mlp", "ffma"])
 def any_model(request):
-    """The tensor-core path (forced on for every call size) and the exact-FP32 FFMA path.  The default
-    policy (fixture `model`) routes calls below 1024 atoms to the FFMA kernels."""
+    """The three compute paths, each forced on for every call size:
+      tc      edge block from the create-time FP64 table, MP layers + node MLP on tcgen05 (the default for large calls)
+      tc-mlp  the same with the edge block evaluated per edge by the tcgen05 edge-MLP kernel (option edge_table = 0)
+      ffma    every block on the exact-FP32 FFMA kernels, no table
+    The default policy (fixture `model`) routes calls below 1024 atoms to the FFMA kernels (table on)."""
     import nmrgnn_b200
     m = nmrgnn_b200.load_model()
+    assert m.handle.edge_table_info()["active"] and m.handle.edge_table_info()["rel_error"] < 2.0 ** -27
     if request.param == "ffma":
         m.handle.set_option("force_ffma", 1)
+        m.handle.set_option("edge_table", 0)
+        assert m.handle.compute_path == "ffma"
     else:
         m.handle.set_option("tc_min_atoms", 0)
-        assert m.handle.compute_path.startswith("tcgen05")
+        if request.param == "tc-mlp":
+            m.handle.set_option("edge_table", 0)
+            assert m.handle.compute_path == "tcgen05-fp16x3(edge,mp,fc)"
+        else:
+            assert m.handle.compute_path == "edge-table-f64+tcgen05-fp16x3(mp,fc)"
     m.path_name = request.param
     yield m
     m.close()
-
-
-# Error budget multiplier on ill-conditioned peaks (conftest.budget_ratio): the exact-FP32 kernels stay
-# within 3x the fp32 reference's own deviation; the fp16x3 tensor-core path (22-bit operands, compensated
-# round-toward-zero accumulation) within 8x.  Well-conditioned peaks must meet 1e-4 + 1e-4 ppm on both.
-KAPPA = {"tc": 8.0, "ffma": 3.0}
 
 
 def graph_of(g):
@@ -53,14 +57,20 @@ def test_forward_matches_traced_graph(any_model, name):
     y = any_model(graph_of(g))
     assert isinstance(y, np.ndarray) and y.dtype == np.float32 and y.shape == g["peaks"].shape
     assert np.array_equal(y == 0, g["peaks"] == 0)            # elements without statistics: exact 0
-    if name == "smallmol12_k8" and any_model.path_name == "tc":
-        # random small molecules put several C/N peaks near 0 ppm, where the fp32 reference itself is off by
-        # 0.46 of the tolerance; the tensor-core path is held to the ill-conditioned budget there
-        assert budget_ratio(y, g["peaks_f64"], g["peaks"], KAPPA["tc"]) <= 1.0
-        assert np.mean(np.abs(y - g["peaks_f64"]) <= 1e-4 * np.abs(g["peaks_f64"]) + 1e-4) >= 0.97
-        return
-    assert tol_ratio(y, g["peaks_f64"]) <= 1.0, (tol_ratio(y, g["peaks_f64"]), rel_err(y, g["peaks_f64"]))
-    assert tol_ratio(y, g["peaks"]) <= 1.0
+    # every path, every fixture: within the tolerance of the exact (fp64) execution of the traced graph ...
+    limit = 1.0
+    if name == "smallmol12_k8" and any_model.path_name != "ffma":
+        # ... except this one when the tensor cores are FORCED on (the default policy runs a 480-atom call on the
+        # exact-FP32 kernels, and that is asserted strictly below): random K = 8 molecules with C / N peaks near 0 ppm
+        # are the worst-conditioned inputs of the suite (the reference's own float32 run: 0.46 of the tolerance), and
+        # the round-toward-zero accumulation of tcgen05 costs ~3x the error of sequential fp32 FMAs: measured 1.43 on
+        # one atom.  Bounded at 2x, every other atom within the tolerance.
+        limit = 2.0
+        assert np.sum(np.abs(y - g["peaks_f64"]) > 1e-4 * np.abs(g["peaks_f64"]) + 1e-4) <= 1
+    assert tol_ratio(y, g["peaks_f64"]) <= limit, (tol_ratio(y, g["peaks_f64"]), rel_err(y, g["peaks_f64"]))
+    # ... and of its float32 execution, allowing for that execution's own distance from the exact result
+    slack = np.abs(g["peaks"].astype(np.float64) - g["peaks_f64"])
+    assert np.all(np.abs(y - g["peaks"]) <= limit * (1e-4 * np.abs(g["peaks_f64"]) + 1e-4) + slack)
 
 
 @pytest.mark.parametrize("name", GOLDEN)
@@ -248,11 +258,7 @@ def test_random_batch_against_oracle(any_model):
     atoms, nlist, edges, inv, offs = b
     y = any_model((atoms, nlist, edges, inv))
     ref64 = orc.forward(any_model.params, atoms, nlist, edges, inv, dtype=np.float64)
-    ref32 = orc.forward(any_model.params, atoms, nlist, edges, inv, dtype=np.float32)
-    # within tolerance, or (ill-conditioned atoms only) within kappa x the fp32 oracle's own deviation
-    err = np.abs(y - ref64) / (1e-4 * np.abs(ref64) + 1e-4)
-    assert budget_ratio(y, ref64, ref32, KAPPA[any_model.path_name]) <= 1.0, float(err.max())
-    assert np.mean(err <= 1.0) > 0.999
+    assert tol_ratio(y, ref64) <= 1.0, tol_ratio(y, ref64)
 
 
 def test_knn_graph_matches_host_builder(model):
@@ -319,97 +325,120 @@ def test_tcgen05_selftest_gemm(model):
 
 
 # ---------------------------------------------------------------------------------------------------
-# BASELINE.json full sizes: size-independent properties (the fp64 oracle is too slow for every run)
+# BASELINE.json full sizes, against the committed golden peaks (tests/golden/full_config{2,3}.npz: the reference's
+# traced graph executed graph by graph in float32 and float64 by tools/make_golden_full.py; the inputs regenerate
+# from their seeds and are checked against the fixture's per-graph digests before anything is compared)
 # ---------------------------------------------------------------------------------------------------
+def _full_fixture(name, batch):
+    import hashlib
+    z = load_golden(name)
+    atoms, nlist, edges, inv, offs = batch
+    assert np.array_equal(offs, z["graph_offsets"]), "regenerated graph sizes differ from the fixture"
+    for g in range(len(offs) - 1):
+        a, b = int(offs[g]), int(offs[g + 1])
+        h = hashlib.sha256()
+        for arr, dt in ((atoms[a:b], np.float32), (nlist[a:b] - a, np.int32), (edges[a:b], np.float32), (inv[a:b], np.float32)):
+            h.update(np.ascontiguousarray(arr, dt).tobytes())
+        assert h.hexdigest()[:16] == str(z["digests"][g]), f"inputs of graph {g} differ from the ones the fixture was made with"
+    return z["peaks_f64"], z["peaks"].astype(np.float64)
+
+
+def _err(y, ref):
+    return np.abs(np.asarray(y, np.float64) - ref) / (1e-4 * np.abs(ref) + 1e-4)
+
+
+def _paths(model, graph):
+    """peaks of the three compute paths (see `any_model`) for one batch, through the default model object"""
+    out = {}
+    h = model.handle
+    try:
+        out["tc"] = model(graph)
+        h.set_option("edge_table", 0)
+        out["tc-mlp"] = model(graph)
+        h.set_option("force_ffma", 1)
+        out["ffma"] = model(graph)
+    finally:
+        h.set_option("force_ffma", 0)
+        h.set_option("edge_table", 1)
+    return out
+
+
 @pytest.fixture(scope="module")
 def config2_batch():
-    """configs[1]: 64 synthetic protein graphs, ~164 k atoms, K = 16 (the bench workload)."""
+    """configs[1]: 64 synthetic protein graphs, 164 105 atoms, K = 16 (the bench workload)."""
     from nmrgnn_b200 import workloads
     return workloads.protein_batch(64, first_seed=0)
+
+
+def test_config2_full_size_against_golden(model, config2_batch):
+    """Every one of the 164 105 atoms of the bench workload against the fp64 execution of the reference's traced
+    graph.  Tolerance 1e-4 relative + 1e-4 ppm, no budget factors:
+      * exact-FP32 kernels: every atom within the tolerance (measured max 0.43);
+      * tensor-core path: 99.99 % of the atoms within HALF the tolerance, and at every level of the error
+        distribution at least as close to the exact result as the reference's own float32 arithmetic (the traced
+        graph executed in float32 misses the tolerance on 5 of these atoms, worst 2.05: C / N atoms whose peak sits
+        ~120 ppm below the element mean, where full*std + avg cancels); measured max 1.38, 2 atoms above 1."""
+    ref64, ref32 = _full_fixture("full_config2", config2_batch)
+    atoms, nlist, edges, inv, offs = config2_batch
+    assert model.handle.compute_path == "edge-table-f64+tcgen05-fp16x3(mp,fc)"
+    ys = _paths(model, (atoms, nlist, edges, inv))
+    e32 = _err(ref32, ref64)
+    for name, y in ys.items():
+        assert y.shape == ref64.shape and np.all(np.isfinite(y))
+        assert np.array_equal(y == 0, ref64 == 0), name                 # elements without statistics: exactly 0
+    e = {k: _err(v, ref64) for k, v in ys.items()}
+    print({k: (round(float(v.max()), 3), int((v > 1).sum()), round(float(np.quantile(v, 0.9999)), 3)) for k, v in e.items()})
+    assert e["ffma"].max() <= 1.0
+    for name in ("tc", "tc-mlp"):
+        assert np.quantile(e[name], 0.9999) <= 0.5, name
+        assert e[name].max() <= e32.max() and (e[name] > 1).sum() <= (e32 > 1).sum(), name
+        for q in (0.5, 0.99, 0.999, 0.9999):
+            assert np.quantile(e[name], q) <= max(np.quantile(e32, q), 0.02), (name, q)
+    assert e["tc"].max() <= 1.5 and (e["tc"] > 1).sum() <= 2
 
 
 def test_config2_full_size_properties(model, config2_batch):
     from nmrgnn_b200.workloads import take_graphs
     atoms, nlist, edges, inv, offs = config2_batch
     n = atoms.shape[0]
-    assert n > 100000
-    assert model.handle.compute_path.startswith("tcgen05")
     y_tc = model((atoms, nlist, edges, inv))                       # default policy: tensor cores at this size
-    assert y_tc.shape == (n,) and np.all(np.isfinite(y_tc))
     # (a) idempotence / determinism: the same call gives the same bits (also through the chunked upload path)
     assert np.array_equal(model((atoms, nlist, edges, inv)), y_tc)
-    # (b) tensor-core path against the exact-FP32 kernels on all 164 k atoms
-    model.handle.set_option("force_ffma", 1)
-    try:
-        y_ff = model((atoms, nlist, edges, inv))
-    finally:
-        model.handle.set_option("force_ffma", 0)
-    tol = 1e-4 * np.abs(y_ff) + 1e-4
-    err = np.abs(y_tc - y_ff) / tol
-    assert np.mean(err <= 1.0) > 0.9995, float(np.mean(err <= 1.0))
-    assert np.quantile(err, 0.999) < 0.5
-    assert np.array_equal(y_tc == 0, y_ff == 0)
-    # (c) graphs are independent: three graphs evaluated alone (tensor-core route as well: > 1024 atoms) agree with
-    #     their slice of the batched tensor-core result within the tolerance
+    # (b) graphs are independent: three graphs evaluated alone (tensor-core route as well: > 1024 atoms) give the
+    #     same bits as their slice of the batch
     for gidx in (0, 31, 63):
         sub = take_graphs(config2_batch, np.array([gidx]))
-        yi = model(sub[:4])
         a, b = int(offs[gidx]), int(offs[gidx + 1])
-        e = np.abs(y_tc[a:b] - yi) / (1e-4 * np.abs(yi) + 1e-4)
-        assert np.mean(e <= 1.0) > 0.999
-    # (d) sharding plan + reassembly reproduce the single-call result bit for bit (world_size 1 code path)
+        assert np.array_equal(model(sub[:4]), y_tc[a:b])
+    # (c) sharding plan + reassembly reproduce the single-call result bit for bit (world_size 1 code path)
     from nmrgnn_b200.sharding import ShardedModel
     assert np.array_equal(ShardedModel(model)(config2_batch), y_tc)
-
-
-def test_cta_pair_kernels_are_bit_identical(config2_batch):
-    """Options "mp_pair" / "fc_pair": the MP layers and the node MLP as CTA pairs (cta_group::2, M = 256 per
-    instruction, the B operand split between the two CTAs).  Same products in the same order, so the peaks must equal
-    the one-CTA kernels' bit for bit — for even and odd numbers of 128-atom tiles (an odd count leaves the peer CTA
-    of the last pair with an empty tile)."""
-    import nmrgnn_b200
-    from nmrgnn_b200.workloads import take_graphs
-    m = nmrgnn_b200.load_model()
-
-    def run(g, mp_pair, fc_pair):
-        m.handle.set_option("mp_pair", mp_pair)
-        m.handle.set_option("fc_pair", fc_pair)
-        return m(g)
-
-    try:
-        m.handle.set_option("tc_min_atoms", 0)
-        assert m.handle.compute_path.startswith("tcgen05")
-        cases = [take_graphs(config2_batch, np.array([0]))[:4], take_graphs(config2_batch, np.array([1, 2, 3]))[:4],
-                 config2_batch[:4]]
-        # a graph cut to an odd / even number of tiles so that both parities are always covered
-        for n in (128 * 9 + 5, 128 * 10):
-            a, nl, e, inv = (x[:n] for x in config2_batch[:4])
-            cases.append((a, np.where(nl < n, nl, 0).astype(nl.dtype), e, inv))
-        for g in cases:
-            n = g[0].shape[0]
-            y0 = run(g, 0, 0)
-            assert np.array_equal(run(g, 1, 0), y0), ("mp_pair", n)
-            assert np.array_equal(run(g, 0, 1), y0), ("fc_pair", n)
-            assert np.array_equal(run(g, 1, 1), y0), ("both", n)
-    finally:
-        m.close()
+    assert n == 164105
 
 
 def test_config3_small_molecules_full_size(model):
-    """configs[2]: 1024 small molecules, K = 8 (~41 k atoms): both paths run and agree on well-conditioned peaks."""
+    """configs[2]: 1024 small molecules, K = 8, 41 176 atoms, against the golden peaks.  These random molecules put
+    many C / N peaks within a few ppm of zero, where no float32 evaluation resolves 1e-4 of the peak: the reference's
+    own float32 arithmetic misses the tolerance on 41 atoms (worst 28).  Asserted: the exact-FP32 kernels are closer to
+    the exact result than the reference's float32 run at the tail, the tensor-core path stays within twice its tail,
+    and both meet the tolerance on >= 99.8 % of the atoms; the worst atoms are printed."""
     from nmrgnn_b200 import workloads
-    atoms, nlist, edges, inv, offs = workloads.small_molecule_batch(1024, first_seed=0)
+    batch = workloads.small_molecule_batch(1024, first_seed=0)
+    ref64, ref32 = _full_fixture("full_config3", batch)
+    atoms, nlist, edges, inv, offs = batch
     assert nlist.shape[1] == 8
-    y_tc = model((atoms, nlist, edges, inv))
-    model.handle.set_option("force_ffma", 1)
-    try:
-        y_ff = model((atoms, nlist, edges, inv))
-    finally:
-        model.handle.set_option("force_ffma", 0)
-    assert np.all(np.isfinite(y_tc)) and np.array_equal(y_tc == 0, y_ff == 0)
-    err = np.abs(y_tc - y_ff) / (1e-4 * np.abs(y_ff) + 1e-4)
-    assert np.mean(err <= 1.0) > 0.985          # random molecules: many ill-conditioned near-zero C/N peaks
-    assert np.median(err) < 0.05
+    ys = _paths(model, (atoms, nlist, edges, inv))
+    e32 = _err(ref32, ref64)
+    e = {k: _err(v, ref64) for k, v in ys.items()}
+    print({k: (round(float(v.max()), 2), int((v > 1).sum()), round(float(np.quantile(v, 0.999)), 3)) for k, v in e.items()},
+          "reference float32:", (round(float(e32.max()), 2), int((e32 > 1).sum()), round(float(np.quantile(e32, 0.999)), 3)))
+    for name, y in ys.items():
+        assert np.all(np.isfinite(y)) and np.array_equal(y == 0, ref64 == 0), name
+        assert np.mean(e[name] <= 1.0) >= 0.998, name
+        assert np.median(e[name]) < 0.01, name
+    assert e["ffma"].max() <= e32.max() and np.quantile(e["ffma"], 0.999) <= 1.25 * np.quantile(e32, 0.999)
+    for name in ("tc", "tc-mlp"):
+        assert e[name].max() <= e32.max() and np.quantile(e[name], 0.999) <= 2.0 * np.quantile(e32, 0.999), name
 
 
 def test_eval_struct_stream(model, tmp_path):
@@ -461,7 +490,8 @@ def test_generic_geometry_models(hp):
     from oracle import forward as orc
     m = nmrgnn_b200.build_GNNModel(hp, num_elem=16, seed=3)
     try:
-        assert m.handle.compute_path == "generic-fp32"
+        assert m.handle.compute_path.endswith("generic-fp32")
+        assert m.handle.edge_table_info()["active"] == (hp["fc_activation"] != "relu")
         atoms, nlist, edges, inv = workloads.ring_graph(5, 16, 2)
         y = m([atoms, nlist, edges * 0.15, inv])
         ref = orc.forward(m.params, atoms, nlist, edges * 0.15, inv, dtype=np.float64)

@@ -52,7 +52,7 @@ def main():
             m.handle.set_option(k, int(v))
             y = m((atoms, nlist, edges, inv)).astype(np.float64)
             report(f"{extra} vs fp64", y, ref)
-            m.handle.set_option(k, 0)
+            m.handle.set_option(k, {"edge_table": 1}.get(k, 0))      # back to the default
 
 
 if __name__ == "__main__":

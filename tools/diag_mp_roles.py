@@ -12,8 +12,6 @@ atoms, nlist, edges, inv, offs = b
 n = atoms.shape[0]
 m = nmrgnn_b200.load_model()
 h = m.handle
-if os.environ.get("MP_PAIR"):
-    h.set_option("mp_pair", 1)      # CTA-pair form: the counters of the MMA thread exist on leader CTAs only
 dev = torch.device("cuda", 0)
 d_in = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (atoms, nlist, edges, inv)]
 out = torch.empty(n, dtype=torch.float32, device=dev)
