@@ -4,10 +4,18 @@ message-passing forward; HBM GB/s / TFLOP/s against the measured B200 roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one forward over one batch of synthetic graphs (config 2 of
-BASELINE.json: 64 protein-like graphs, ~2 500 atoms each, 16-wide neighbour list,
-pretrained weights).  N > 1 (torchrun): every rank owns its own 64-graph shard
-(weak scaling), runs the same forward and the ranks all-gather their peaks (NCCL).
+One "step" = one forward over one batch of synthetic graphs.  --config selects the BASELINE.json configuration
+(numbered as in BASELINE.md, 1-based):
+  2 (default)  64 protein-like graphs (~2 500 atoms, 16-wide neighbour list) PER GPU: weak scaling over N
+  3            1 024 small molecules (~40 atoms, 8-wide neighbour list), sharded by graph over N (strong scaling)
+  4            1 024 protein graphs sharded by graph over N GPUs (strong scaling; --graphs-total G for other sizes)
+  5            MD stream: 108M.pdb x 512 jittered frames, graph build + forward per frame batch, frames round-robin
+               over N GPUs (metric: frames/s; per-frame latency reported)
+N > 1 (torchrun, one rank per GPU): every rank runs the forward on its graphs and the peaks of all ranks are
+reassembled on every rank by the library's peer-memory exchange (nmrgnn_forward_sharded: stores over NVLink +
+epoch flags, no collective-library call; --collective nccl times torch.distributed's all-gather instead).
+At every N the default run also measures config 4 (field `config4_strong`) so that a 1..8 GPU sweep carries the
+strong-scaling numbers; --no-config4 skips it.
 
 Prints ONE JSON line (rank 0).  `value` = atoms/s with inputs resident in HBM;
 `e2e` = the same through the public host-array API (pinned host buffers, H2D and
@@ -38,8 +46,8 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 
 def mp_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one MP-layer launch from the committed ncu capture
-    (profiles/r01_mp_traffic.json; same workload).  None if no capture is on record."""
-    path = os.path.join(ROOT, "profiles", "r01_mp_traffic.json")
+    (profiles/r02_mp_traffic.json; same workload).  None if no capture is on record."""
+    path = os.path.join(ROOT, "profiles", "r02_mp_traffic.json")
     try:
         with open(path) as f:
             d = json.load(f)
@@ -131,27 +139,45 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_workload(rank: int, n_graphs: int, world: int = 1, graphs_total: int = 0):
-    """Weak scaling (default): every rank generates its own `n_graphs` graphs (seeds rank*n .. rank*n+n-1).
-    Strong scaling (--graphs-total G, BASELINE config 4): the G graphs with seeds 0..G-1 are assigned to ranks by the
-    greedy atom-count balance of nmrgnn_b200.sharding.ShardPlan; a rank only generates the graphs it owns."""
+def make_workload(rank: int, world: int, config: int, graphs_total: int = 0):
+    """This rank's graphs of the selected configuration (a rank only generates the graphs it owns).
+    config 2: weak scaling, seeds rank*64 .. rank*64+63.  configs 3 / 4: the G graphs with seeds 0..G-1 assigned to
+    ranks by the greedy atom-count balance of nmrgnn_b200.sharding.ShardPlan."""
     from nmrgnn_b200 import workloads
-    if graphs_total <= 0:
-        return workloads.protein_batch(n_graphs, first_seed=rank * n_graphs, neighbor_number=K_NEIGH)
     from nmrgnn_b200.graph import batch_graphs
     from nmrgnn_b200.sharding import ShardPlan
-    sizes = np.array([workloads.protein_graph_size(s) for s in range(graphs_total)], np.int64)
+    if config == 2 and graphs_total <= 0:
+        return workloads.protein_batch(GRAPHS_PER_GPU, first_seed=rank * GRAPHS_PER_GPU, neighbor_number=K_NEIGH)
+    if config == 3:
+        total = graphs_total or 1024
+        sizes = np.array([workloads.small_molecule_graph(s)[0].shape[0] for s in range(total)], np.int64) if world > 1 else None
+        if world == 1:
+            return workloads.small_molecule_batch(total, first_seed=0)
+        plan = ShardPlan(np.concatenate([[0], np.cumsum(sizes)]), world)
+        return batch_graphs([workloads.small_molecule_graph(int(g)) for g in plan.owned[rank]])
+    total = graphs_total or 1024
+    sizes = np.array([workloads.protein_graph_size(s) for s in range(total)], np.int64)
     plan = ShardPlan(np.concatenate([[0], np.cumsum(sizes)]), world)
     graphs = workloads.protein_graphs([int(g) for g in plan.owned[rank]], neighbor_number=K_NEIGH)
     return batch_graphs(graphs)
 
 
-def workload_config(n_gpus, **extra):
-    cfg = {"workload": f"config[1]: batch of {GRAPHS_PER_GPU} synthetic protein graphs (~2500 atoms, 16-wide nlist), "
-                       f"fp32, pretrained weights, per GPU",
-           "graphs_per_gpu": GRAPHS_PER_GPU, "neighbor_number": K_NEIGH,
-           "parallelism": f"graph-sharded x{n_gpus}, all-gather of peaks" if n_gpus > 1 else "single GPU",
-           "l2_policy": "per-step working set (inputs 28 MB + node/edge buffers ~360 MB) exceeds the 126 MB L2"}
+WORKLOAD_TEXT = {
+    2: "config[1]: batch of {g} synthetic protein graphs (~2500 atoms, 16-wide nlist), fp32, pretrained weights, per GPU",
+    3: "config[2]: batch of {g} small-molecule graphs (~40 atoms, 8-wide nlist), fp32, sharded by graph over {n} GPU(s)",
+    4: "config[3]: batch of {g} synthetic protein graphs sharded by graph over {n} GPU(s), peaks reassembled on every rank",
+    5: "config[4]: MD trajectory stream, 108M.pdb x {g} jittered frames, graph build + forward per frame batch, "
+       "frames round-robin over {n} GPU(s)",
+}
+
+
+def workload_config(n_gpus, config=2, graphs=GRAPHS_PER_GPU, **extra):
+    cfg = {"workload": WORKLOAD_TEXT[config].format(g=graphs, n=n_gpus),
+           "parallelism": (f"graph-sharded x{n_gpus}, peaks reassembled over peer memory (NVLink)" if n_gpus > 1 else "single GPU"),
+           "l2_policy": "per-step working set (inputs + node / edge-record buffers, ~2.3 KB per atom) exceeds the 126 MB L2 "
+                        "for configs 2 and 4; configs 3 and 5 fit and say so in `l2_note`"}
+    if config == 2:
+        cfg.update(graphs_per_gpu=GRAPHS_PER_GPU, neighbor_number=K_NEIGH)
     cfg.update(extra)
     return cfg
 
@@ -166,11 +192,18 @@ def run_reference(args):
         return
     import torch
     from nmrgnn_b200.params import GNNParams, baseline_path
+    from nmrgnn_b200.workloads import take_graphs
     from oracle.forward_torch import TorchReference
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_graphs = 2
-    batch = make_workload(0, sample_graphs)
+    if args.config == 3:
+        from nmrgnn_b200 import workloads
+        batch = workloads.small_molecule_batch(64, first_seed=0)
+        what = "64 molecules"
+    else:
+        from nmrgnn_b200 import workloads
+        batch = workloads.protein_batch(2, first_seed=0, neighbor_number=K_NEIGH)
+        what = "2 graphs"
     n_atoms = int(batch[0].shape[0])
     ref = TorchReference(GNNParams.load(baseline_path()), reference_order=True)
     for _ in range(args.warmup):
@@ -180,20 +213,25 @@ def run_reference(args):
         ref.per_graph(batch)
     dt = (time.perf_counter() - t0) / args.steps
     value = n_atoms / dt
-    sample = (f"{sample_graphs} graphs ({n_atoms} atoms) of the config-2 workload per step, one graph per call, "
-              f"torch {torch.__version__} CPU fp32, reference einsum order")
+    unit, metric = "atoms/s", "atoms/sec MP-GNN forward"
+    if args.config == 5:        # one frame = one 108M-sized graph
+        value, unit, metric = value / 2482.0, "frames/s", "frames/sec MD-stream inference (108M.pdb-sized frames)"
+    sample = (f"{what} ({n_atoms} atoms) of the workload per step, one graph per call, "
+              f"torch {torch.__version__} CPU fp32, reference einsum order (graph build not included)")
     print(json.dumps({
-        "impl": "reference", "metric": "atoms/sec MP-GNN forward", "value": value, "unit": "atoms/s",
+        "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, sample=sample),
-        "cpu_baseline": {"value": value, "unit": "atoms/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "atoms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "weak" if args.config == 2 else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args.gpus, args.config, {2: GRAPHS_PER_GPU, 3: 1024, 4: args.graphs_total or 1024, 5: 512}[args.config],
+                                  sample=sample),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def cpu_baseline(batch, budget_s=12.0):
+def cpu_baseline(batch, budget_s=12.0, n_graphs=2):
     import torch
     from nmrgnn_b200.params import GNNParams, baseline_path
     from nmrgnn_b200.workloads import take_graphs
@@ -201,7 +239,7 @@ def cpu_baseline(batch, budget_s=12.0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     ref = TorchReference(GNNParams.load(baseline_path()), reference_order=True)
-    sub = take_graphs(batch, np.arange(2))
+    sub = take_graphs(batch, np.arange(n_graphs))
     ref.per_graph(sub)                      # warm-up
     best, n_runs, t_start = None, 0, time.perf_counter()
     while n_runs < 5 and (time.perf_counter() - t_start) < budget_s:
@@ -212,15 +250,199 @@ def cpu_baseline(batch, budget_s=12.0):
         n_runs += 1
     n_atoms = int(sub[0].shape[0])
     return {"value": n_atoms / best, "unit": "atoms/s", "cores": cores, "kind": "port",
-            "sample": f"first 2 graphs ({n_atoms} atoms) of the workload, one graph per call, best of {n_runs}; "
+            "sample": f"first {n_graphs} graphs ({n_atoms} atoms) of the workload, one graph per call, best of {n_runs}; "
                       f"torch-CPU restatement of the reference in its einsum order (TensorFlow not installable)"}
+
+
+class Bench:
+    """Device / e2e timing of one sharded workload on this rank (shared by the main measurement and `config4_strong`)."""
+
+    def __init__(self, model, batch, world, rank, dev, collective):
+        import torch
+        import torch.distributed as dist
+        from nmrgnn_b200 import _capi
+        from nmrgnn_b200.sharding import PeerGather
+        self.torch, self.dist, self.capi = torch, dist, _capi
+        self.model, self.h, self.world, self.rank, self.dev = model, model.handle, world, rank, dev
+        self.collective = collective
+        atoms, nlist, edges, inv, offs = batch
+        self.n_atoms = int(atoms.shape[0])
+        self.k = int(nlist.shape[1])
+        self.n_graphs = len(offs) - 1
+        self.d_in = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (atoms, nlist, edges, inv)]
+        self.pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (atoms, nlist, edges, inv)]
+        self.pin_np = [t.numpy() for t in self.pin]
+        self.h2d = sum(t.numel() * t.element_size() for t in self.pin)
+        counts = [self.n_atoms]
+        if world > 1:
+            c = torch.tensor([self.n_atoms], device=dev, dtype=torch.int64)
+            allc = [torch.zeros_like(c) for _ in range(world)]
+            dist.all_gather(allc, c)
+            counts = [int(x.item()) for x in allc]
+        self.counts = counts
+        self.total_atoms = sum(counts)
+        self.max_n = max(counts)
+        self.stream = torch.cuda.current_stream(dev)
+        self.sptr = int(self.stream.cuda_stream) or 1
+        if world > 1 and collective == "peer":
+            self.pg = PeerGather(model, self.max_n)
+            cap = self.pg.capacity
+            self.out_pin = torch.empty(world * cap, dtype=torch.float32).pin_memory()
+        else:
+            self.pg = None
+            self.d_peaks = torch.zeros(self.max_n, dtype=torch.float32, device=dev)
+            self.gather_out = torch.empty(world * self.max_n, dtype=torch.float32, device=dev) if world > 1 else None
+            self.out_pin = torch.empty(world * self.max_n if world > 1 else self.n_atoms, dtype=torch.float32).pin_memory()
+        self.out_np = self.out_pin.numpy()
+        self.d2h = self.out_pin.numel() * 4
+
+    def step_device(self):
+        h, d, c = self.h, self.d_in, self.capi
+        if self.pg is not None:
+            h.forward_sharded(d[0], d[1], d[2], d[3], self.n_atoms, self.k, None, c.MEM_DEVICE, self.sptr)
+        else:
+            h.forward(d[0], d[1], d[2], d[3], self.n_atoms, self.k, self.d_peaks, c.MEM_DEVICE, self.sptr)
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self.gather_out, self.d_peaks)
+
+    def step_e2e(self):
+        h, p, c = self.h, self.pin_np, self.capi
+        if self.pg is not None:       # host buffers in, every rank's peaks back in host memory: copies + exchange inside
+            h.forward_sharded(p[0], p[1], p[2], p[3], self.n_atoms, self.k, self.out_np, c.MEM_HOST, None)
+        elif self.world > 1:
+            tmp = self.out_np[:self.n_atoms]
+            h.forward(p[0], p[1], p[2], p[3], self.n_atoms, self.k, tmp, c.MEM_HOST, None)
+            self.d_peaks[:self.n_atoms].copy_(self.out_pin[:self.n_atoms], non_blocking=True)
+            self.dist.all_gather_into_tensor(self.gather_out, self.d_peaks)
+            self.out_pin.copy_(self.gather_out, non_blocking=True)
+            self.torch.cuda.synchronize(self.dev)
+        else:
+            h.forward(p[0], p[1], p[2], p[3], self.n_atoms, self.k, self.out_np, c.MEM_HOST, None)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps, sampler=None):
+        torch = self.torch
+        self.barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None
+        return e0.elapsed_time(e1), wall * 1e3, clocks
+
+    def reduce_max(self, *vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.pg is not None:
+            self.h.synchronize(self.sptr)
+            self.barrier()
+            self.h.comm_destroy()
+
+
+def run_md_stream(args, model, world, rank, local_rank, dev):
+    """config 5: 108M.pdb x 512 frames (seeded Gaussian jitter, sigma = 0.02 nm), graph build on the GPU + forward per
+    frame batch, frames round-robin over the ranks.  `value` = frames/s from positions resident in pinned host memory
+    to peaks in host memory (that IS the end-to-end path of a trajectory: there is no device-resident variant of a
+    stream), `device` = the compute stream's time alone."""
+    import torch
+    import torch.distributed as dist
+    from nmrgnn_b200.mdstream import FrameStream
+    n_frames = 512
+    with np.load(os.path.join(ROOT, "tests", "golden", "g108m_structure.npz")) as z:
+        pos = z["positions_A"].astype(np.float32) / np.float32(10)
+        elements = [str(e) for e in z["elements"]]
+    rng = np.random.default_rng(0)
+    frames = pos[None] + rng.normal(scale=0.02, size=(n_frames,) + pos.shape).astype(np.float32)
+    fs = FrameStream(model, elements, pos.shape[0], K_NEIGH)
+    for _ in range(max(args.warmup, 3)):
+        fs.run(frames[:4 * fs.B], 0, 1)
+    steps = max(1, min(args.steps, 20))
+    l0 = model.handle.kernel_launches
+    walls, devs = [], []
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.start()
+    for _ in range(steps):
+        if world > 1:
+            dist.barrier()
+        r = fs.run(frames, rank, world)
+        walls.append(r["seconds"])
+        devs.append(r["device_ms"] * 1e-3)
+    clocks = sampler.stop() if sampler else None
+    wall, devt = float(np.mean(walls)), float(np.mean(devs))
+    if world > 1:
+        t = torch.tensor([wall, devt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall, devt = float(t[0]), float(t[1])
+    # where a batch's device time goes: graph build alone vs forward alone, same buffers, plain launches
+    from nmrgnn_b200 import _capi
+    hh, sp = model.handle, int(fs.compute.cuda_stream)
+    split = {}
+    with torch.cuda.stream(fs.compute):
+        for name, fn in (("knn_graph", lambda: hh.knn_graph(fs.d_pos[0], fs.offsets, fs.B * fs.n, fs.B, fs.k, 0.0, fs.d_nlist, fs.d_edges,
+                                                             fs.d_inv, _capi.MEM_DEVICE, sp)),
+                         ("forward", lambda: hh.forward(fs.d_atoms, fs.d_nlist, fs.d_edges, fs.d_inv, fs.B * fs.n, fs.k, fs.d_peaks[0],
+                                                        _capi.MEM_DEVICE, sp))):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fn()
+            e0.record(fs.compute)
+            for _ in range(20):
+                fn()
+            e1.record(fs.compute)
+            fs.compute.synchronize()
+            split[name + "_ms_per_batch"] = e0.elapsed_time(e1) / 20
+    # single-frame latency: one frame per launch, no batching (what an interactive caller sees)
+    one = FrameStream(model, elements, pos.shape[0], K_NEIGH, frames_per_batch=1)
+    one.run(frames[:8])
+    lat = one.run(frames[:64])
+    if rank == 0:
+        n = pos.shape[0]
+        line = {
+            "metric": "frames/sec MD-stream inference (108M.pdb-sized frames)", "value": n_frames / wall, "unit": "frames/s",
+            "atoms_per_s": n_frames * n / wall, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (108M.pdb coordinates + seeded jitter)",
+            "config": workload_config(world, 5, n_frames, atoms_per_frame=n, frames_per_batch=fs.B, cuda_graph=fs.graph_captured,
+                                      compute_path=model.handle.compute_path,
+                                      l2_note="one batch (8 frames) is 46 MB of node / record buffers: L2-resident; frames "
+                                              "differ from batch to batch"),
+            "clocks": clocks,
+            "device": {"frames_per_s": n_frames / devt, "ms_per_frame": devt * 1e3 / n_frames,
+                       "note": "compute stream only (graph build + forward), max over ranks", **split},
+            "latency": {"ms_per_frame_unbatched": lat["seconds"] * 1e3 / 64, "ms_per_batch": wall * 1e3 / max(1, -(-n_frames // fs.B) // world),
+                        "frames_per_batch": fs.B},
+            "e2e": {"value": n_frames / wall, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes // world),
+                    "d2h_bytes_per_step": int(n_frames * n * 4 // world),
+                    "api": "FrameStream.run (nmrgnn_knn_graph + nmrgnn_forward, CUDA graph per batch, pinned staging)"},
+            "gpu_launches": int(model.handle.kernel_launches - l0),
+            "gpu_launches_note": "kernels enqueued through the C ABI while capturing; graph replays re-launch 7 kernels per batch",
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line))
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import nmrgnn_b200
-    from nmrgnn_b200 import _capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,110 +452,91 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-
-    batch = make_workload(rank, GRAPHS_PER_GPU, world, args.graphs_total)
-    atoms, nlist, edges, inv, offs = batch
-    n_atoms = int(atoms.shape[0])
     model = nmrgnn_b200.load_model(device=local_rank)
     h = model.handle
-
-    # device-resident inputs for `value`; pinned host copies for `e2e`
-    d_in = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (atoms, nlist, edges, inv)]
-    d_peaks = torch.empty(n_atoms, dtype=torch.float32, device=dev)
-    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in (atoms, nlist, edges, inv)]
-    pin_np = [t.numpy() for t in pin]
-    out_pin = torch.empty(n_atoms, dtype=torch.float32).pin_memory()
-    out_np = out_pin.numpy()
-    h2d = sum(t.numel() * t.element_size() for t in pin)
-    d2h = out_pin.numel() * 4
-
-    # all-gather plumbing (N > 1): padded to the largest shard
-    counts = [n_atoms]
-    if world > 1:
-        c = torch.tensor([n_atoms], device=dev, dtype=torch.int64)
-        allc = [torch.zeros_like(c) for _ in range(world)]
-        dist.all_gather(allc, c)
-        counts = [int(x.item()) for x in allc]
-    max_n = max(counts)
-    gather_in = torch.zeros(max_n, dtype=torch.float32, device=dev)
-    gather_out = torch.empty(world * max_n, dtype=torch.float32, device=dev) if world > 1 else None
-
-    stream = torch.cuda.current_stream(dev)
-    sptr = int(stream.cuda_stream) or 1
-
-    def step_device():
-        h.forward(d_in[0], d_in[1], d_in[2], d_in[3], n_atoms, K_NEIGH, gather_in if world > 1 else d_peaks,
-                  _capi.MEM_DEVICE, sptr)
-        if world > 1:
-            dist.all_gather_into_tensor(gather_out, gather_in)
-
-    def step_e2e():
-        h.forward(pin_np[0], pin_np[1], pin_np[2], pin_np[3], n_atoms, K_NEIGH, out_np, _capi.MEM_HOST, None)
-
-    def barrier():
+    if args.config == 5:
+        run_md_stream(args, model, world, rank, local_rank, dev)
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize(dev)
+            dist.destroy_process_group()
+        return
 
-    def timed(fn, steps, sampler=None):
-        barrier()
-        if sampler:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        clocks = sampler.stop() if sampler else None
-        ms = e0.elapsed_time(e1)
-        return ms, wall * 1e3, clocks
+    config = 4 if (args.graphs_total > 0 and args.config == 2) else args.config
+    batch = make_workload(rank, world, config, args.graphs_total)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        cpu = cpu_baseline(batch, n_graphs=64 if config == 3 else 2)     # before any rank spins in a barrier (N = 1 only)
+    b = Bench(model, batch, world, rank, dev, args.collective)
+    n_atoms = b.n_atoms
 
     for _ in range(max(args.warmup, 3)):
-        step_device()
-    h.synchronize(sptr)
+        b.step_device()
+    h.synchronize(b.sptr)
     l0 = h.kernel_launches
-    ms_dev, _, clocks = timed(step_device, args.steps, ClockSampler(local_rank) if rank == 0 else None)
+    ms_dev, _, clocks = b.timed(b.step_device, args.steps, ClockSampler(local_rank) if rank == 0 else None)
     launches = h.kernel_launches - l0
-    h.synchronize(sptr)
+    h.synchronize(b.sptr)
 
-    # e2e: the host API is synchronous, so the wall clock covers copies + kernels
+    # e2e: the host API is synchronous, so the wall clock covers copies + kernels (+ the exchange for N > 1)
     for _ in range(3):
-        step_e2e()
-    _, wall_e2e, _ = timed(step_e2e, args.steps)
+        b.step_e2e()
+    _, wall_e2e, _ = b.timed(b.step_e2e, args.steps)
 
     # per-kernel timing for the roofline object: CUDA events recorded by the library on the launching
     # stream around each stage of the same forward (option "profile"), averaged over the timed steps
     h.set_option("profile", 1)
     acc = None
     for _ in range(args.steps):
-        step_device()
+        b.step_device()
         st = h.stage_times()
         flat = [st["edge"], st["embed"]] + list(st["mp_layers"]) + [st["fc_readout"]]
-        acc = flat if acc is None else [a + b for a, b in zip(acc, flat)]
+        acc = flat if acc is None else [a + c for a, c in zip(acc, flat)]
     h.set_option("profile", 0)
     acc = [a / args.steps for a in acc]
     n_mp = len(acc) - 3
     kern = {"edge": acc[0], "embed": acc[1], "mp_layer": sum(acc[2:2 + n_mp]) / n_mp, "fc_readout": acc[-1]}
-    h.synchronize(sptr)
+    h.synchronize(b.sptr)
 
-    # max over ranks of the device time
+    # the same step with the edge block evaluated per edge by the tcgen05 edge-MLP kernel instead of the table
+    h.set_option("edge_table", 0)
+    for _ in range(3):
+        b.step_device()
+    ms_mlp, _, _ = b.timed(b.step_device, min(args.steps, 10))
+    ms_mlp /= min(args.steps, 10)
+    path_mlp = h.compute_path
+    h.set_option("edge_table", 1)
+    ms_dev, wall_e2e, ms_mlp = b.reduce_max(ms_dev, wall_e2e, ms_mlp)
+    total_atoms, total_graphs = b.total_atoms, None
     if world > 1:
-        t = torch.tensor([ms_dev, wall_e2e], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, wall_e2e = float(t[0]), float(t[1])
-        tot = torch.tensor([n_atoms], device=dev, dtype=torch.int64)
-        dist.all_reduce(tot)
-        total_atoms = int(tot.item())
+        tg = torch.tensor([b.n_graphs], device=dev, dtype=torch.int64)
+        dist.all_reduce(tg)
+        total_graphs = int(tg.item())
     else:
-        total_atoms = n_atoms
+        total_graphs = b.n_graphs
+    h2d, d2h = b.h2d, b.d2h
+    compute_path = h.compute_path
+    b.close()
+
+    # strong scaling on config 4 (1 024 protein graphs over the same N ranks) as an extra field of this line
+    c4 = None
+    if config == 2 and not args.no_config4:
+        batch4 = make_workload(rank, world, 4, 1024)
+        b4 = Bench(model, batch4, world, rank, dev, args.collective)
+        for _ in range(3):
+            b4.step_device()
+        s4 = 5
+        ms4, _, _ = b4.timed(b4.step_device, s4)
+        (ms4,) = b4.reduce_max(ms4)
+        c4 = {"workload": WORKLOAD_TEXT[4].format(g=1024, n=world), "total_atoms": b4.total_atoms, "ms_per_step": ms4 / s4,
+              "value": b4.total_atoms / (ms4 / s4 * 1e-3), "unit": "atoms/s", "steps": s4, "scaling": "strong",
+              "atoms_on_largest_rank": b4.max_n}
+        b4.close()
 
     if rank == 0:
         peaks = measured_peaks()
-        fl = flops_per_atom(K_NEIGH)
-        by = bytes_per_atom(K_NEIGH)
+        K = b.k
+        fl = flops_per_atom(K)
+        by = bytes_per_atom(K)
         ms_step = ms_dev / args.steps
         value = total_atoms / (ms_step * 1e-3)
         e2e_ms = wall_e2e / args.steps
@@ -342,10 +545,10 @@ def run_ours(args):
         mp_gbs = (n_atoms * by["mp_layer"] + 4 * 256 * 256 * 3) / t_mp / 1e9
         step_kernel_ms = kern["edge"] + kern["embed"] + 4 * kern["mp_layer"] + kern["fc_readout"]
         roofline = {
-            "kernel": "mp_layer (" + h.compute_path + ")", "bound": "tensor",
+            "kernel": "mp_layer_tc_kernel (one of 4 launches per step; " + compute_path + ")", "bound": "tensor",
             "achieved": mp_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": mp_tflops / peaks["bf16_tflops"], "traffic": mp_traffic_bytes(),
-            "traffic_note": "ncu dram bytes of one MP-layer launch (profiles/r01_final_ncu_summary.md); algorithmic "
+            "frac": mp_tflops / peaks["bf16_tflops"], "traffic": mp_traffic_bytes() if config == 2 else None,
+            "traffic_note": "ncu dram bytes of one MP-layer launch on config 2 (profiles/r02_mp_traffic.json); algorithmic "
                             "bytes of the launch = atoms_per_gpu * 2308 + 786432",
             "peak_source": peaks["_source"] + " bf16 dense (MEASURED_PEAKS.json); achieved counts ALGORITHMIC flops: the "
                            "path needs fp32-accurate products and executes every one as three fp16 tensor-core products "
@@ -356,27 +559,41 @@ def run_ours(args):
                     "bytes_per_atom": by["mp_layer"]},
             "flops_per_atom": fl["mp_layer"],
             "kernels_ms": kern,
-            "whole_forward": {"tflops": total_atoms / world * fl["total"] / (ms_step * 1e-3) / 1e12,
-                              "flops_per_atom": fl["total"], "bytes_per_atom": by["total"]},
+            "whole_forward": {"tflops": total_atoms / world * (fl["total"] - fl["edge"]) / (ms_step * 1e-3) / 1e12,
+                              "flops_per_atom": fl["total"] - fl["edge"], "bytes_per_atom": by["total"],
+                              "note": "the edge MLP's flops (K * 99 072 per atom) are not executed on the table path and "
+                                      "not counted here"},
         }
-        cpu = None if args.skip_cpu_baseline else cpu_baseline(batch)
+        graphs = {2: GRAPHS_PER_GPU, 3: total_graphs, 4: total_graphs}[config]
+        extra = {}
+        if config in (3, 4):
+            extra["graphs_total"] = total_graphs
+        if config == 3:
+            extra["l2_note"] = "41 k atoms: the 95 MB per-step working set fits the 126 MB L2 (inputs are re-read from it every step)"
         line = {
             "metric": "atoms/sec MP-GNN forward", "value": value, "unit": "atoms/s",
-            "graphs_per_s": (args.graphs_total if args.graphs_total > 0 else world * GRAPHS_PER_GPU) / (ms_step * 1e-3),
+            "graphs_per_s": (total_graphs if config != 2 else world * GRAPHS_PER_GPU) / (ms_step * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "strong" if args.graphs_total > 0 else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if config == 2 else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world, atoms_per_gpu=n_atoms, total_atoms=total_atoms,
-                                      compute_path=h.compute_path,
-                                      **({"workload": f"config[3]: batch of {args.graphs_total} synthetic protein graphs "
-                                                      f"sharded by graph over {world} GPU(s), all-gather of peaks",
-                                          "graphs_total": args.graphs_total} if args.graphs_total > 0 else {})),
+            "config": workload_config(world, config, graphs, atoms_per_gpu=n_atoms, total_atoms=total_atoms,
+                                      compute_path=compute_path, neighbor_number=K,
+                                      collective=("none" if world == 1 else
+                                                  "peer-memory exchange inside nmrgnn_forward_sharded (NVLink stores + epoch flags)"
+                                                  if args.collective == "peer" else "torch.distributed all_gather_into_tensor (NCCL)"),
+                                      **extra),
             "clocks": clocks,
             "e2e": {"value": total_atoms / (e2e_ms * 1e-3), "unit": "atoms/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "nmrgnn_forward(NMRGNN_MEM_HOST) with pinned host buffers"},
+                    "api": ("nmrgnn_forward_sharded(NMRGNN_MEM_HOST): pinned host buffers in, every rank's peaks back in host "
+                            "memory" if world > 1 and args.collective == "peer" else
+                            "nmrgnn_forward(NMRGNN_MEM_HOST) with pinned host buffers")},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "edge_mlp_variant": {"compute_path": path_mlp, "ms_per_step": ms_mlp, "value": total_atoms / (ms_mlp * 1e-3),
+                                 "unit": "atoms/s", "note": "option edge_table = 0: the edge block evaluated per edge by the "
+                                                            "tcgen05 edge-MLP kernel instead of the create-time FP64 table"},
+            "config4_strong": c4,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
@@ -391,9 +608,13 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (1-based)")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: the library's peer-memory exchange (default) or torch.distributed's NCCL all-gather")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="profiling runs only (ncu)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the extra config-4 strong-scaling measurement")
     ap.add_argument("--graphs-total", type=int, default=0,
-                    help="strong scaling: a fixed batch of this many graphs sharded over the ranks (BASELINE config 4 = 1024)")
+                    help="configs 3 / 4: number of graphs in the fixed batch (default 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -41,7 +41,8 @@ typedef enum nmrgnn_status {
   NMRGNN_ERR_BAD_INDEX = -2,  /* nlist entry outside [0, n_atoms) (TF GatherV2 raises) */
   NMRGNN_ERR_CUDA = -3,       /* CUDA runtime error; message in nmrgnn_last_error      */
   NMRGNN_ERR_OOM = -4,        /* device allocation failed                              */
-  NMRGNN_ERR_NO_DEVICE = -5   /* no sm_100 device / kernels not loadable               */
+  NMRGNN_ERR_NO_DEVICE = -5,  /* no sm_100 device / kernels not loadable               */
+  NMRGNN_ERR_COMM = -6        /* a peer's gather buffer cannot be mapped (multi-GPU)   */
 } nmrgnn_status;
 
 enum { NMRGNN_MEM_HOST = 0, NMRGNN_MEM_DEVICE = 1 };
@@ -99,6 +100,31 @@ void nmrgnn_destroy(nmrgnn_handle* h);
 int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
                    const float* inv_degree, int64_t n_atoms, int32_t k, float* peaks,
                    int mem, void* stream);
+
+/* ---- Multi-GPU: batches of independent graphs sharded by whole graphs, one process per GPU ---------------
+ * The reference has no multi-device code; graphs never interact (tf.gather indexes inside one graph,
+ * nmrgnn/layers.py:33), so the only exchange of the path is "every rank gets every rank's peaks".  It is done
+ * over peer memory (NVLink / NVSwitch) by the library's own kernels, without a collective-library call: every
+ * rank stores its peaks into its slot of EVERY rank's gather buffer, publishes the call's epoch with a
+ * system-scope release, and a wait kernel on the same stream acquires all sources (csrc/peer_gather.cuh).
+ *
+ *   1. every rank: nmrgnn_comm_local(h, capacity, world, blob)   capacity >= the largest shard (atoms);
+ *      allocates this rank's buffers, writes NMRGNN_COMM_HANDLE_BYTES of CUDA IPC handles to `blob`
+ *   2. exchange the blobs by any means (torch.distributed / MPI all-gather of bytes; rank order)
+ *   3. every rank: nmrgnn_comm_init(h, rank, world, all_blobs)   maps the other ranks' buffers
+ *   4. per batch, every rank: nmrgnn_forward_sharded(local shard ..., gathered, mem, stream)
+ * `gathered` (may be NULL) receives float [world][capacity_4] (capacity rounded up to a multiple of 4; rank
+ * r's peaks are the first n_r entries of row r) in the memory space `mem`; nmrgnn_comm_buffer returns the
+ * device-resident copy of the latest call.  A rank with n_local = 0 still calls.  All ranks must make the
+ * same sequence of calls.  world = 1 works without peers (steps 2 and IPC are no-ops). */
+#define NMRGNN_COMM_HANDLE_BYTES 128
+int nmrgnn_comm_local(nmrgnn_handle* h, int64_t capacity, int32_t world, void* ipc_out);
+int nmrgnn_comm_init(nmrgnn_handle* h, int32_t rank, int32_t world, const void* all_ipc);
+int nmrgnn_forward_sharded(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
+                           const float* inv_degree, int64_t n_local, int32_t k, float* gathered,
+                           int mem, void* stream);
+const float* nmrgnn_comm_buffer(nmrgnn_handle* h, int64_t* capacity);
+void nmrgnn_comm_destroy(nmrgnn_handle* h);
 
 /* Per-block entry points (same `mem`/`stream` rules), one per reference layer,
  * used by the parity tests and by callers that compose their own model. */

@@ -15,13 +15,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libnmrgnn_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-OK, ERR_BAD_DIMS, ERR_BAD_INDEX, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE = 0, -1, -2, -3, -4, -5
+OK, ERR_BAD_DIMS, ERR_BAD_INDEX, ERR_CUDA, ERR_OOM, ERR_NO_DEVICE, ERR_COMM = 0, -1, -2, -3, -4, -5, -6
+COMM_HANDLE_BYTES = 128
 
 EXPORTS = [
     "nmrgnn_abi_version", "nmrgnn_num_weights", "nmrgnn_create", "nmrgnn_destroy", "nmrgnn_forward",
     "nmrgnn_edge_features", "nmrgnn_embed", "nmrgnn_mp_layer", "nmrgnn_fc_readout", "nmrgnn_synchronize",
     "nmrgnn_kernel_launches", "nmrgnn_compute_path", "nmrgnn_last_error", "nmrgnn_knn_graph",
     "nmrgnn_set_option", "nmrgnn_selftest_gemm", "nmrgnn_stage_times", "nmrgnn_tc_compensation", "nmrgnn_edge_table_info",
+    "nmrgnn_comm_local", "nmrgnn_comm_init", "nmrgnn_forward_sharded", "nmrgnn_comm_buffer", "nmrgnn_comm_destroy",
 ]
 
 
@@ -74,6 +76,13 @@ def load_library() -> C.CDLL:
     lib.nmrgnn_stage_times.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.nmrgnn_tc_compensation.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.nmrgnn_edge_table_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    lib.nmrgnn_comm_local.argtypes = [vp, i64, i32, vp]
+    lib.nmrgnn_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.nmrgnn_forward_sharded.argtypes = [vp, fp, fp, fp, fp, i64, i32, fp, C.c_int, vp]
+    lib.nmrgnn_comm_buffer.argtypes = [vp, C.POINTER(i64)]
+    lib.nmrgnn_comm_buffer.restype = C.c_void_p
+    lib.nmrgnn_comm_destroy.argtypes = [vp]
+    lib.nmrgnn_comm_destroy.restype = None
     if lib.nmrgnn_abi_version() != 1:
         raise ImportError("libnmrgnn_b200.so ABI version mismatch")
     _lib = lib
@@ -153,6 +162,30 @@ class Handle:
         if n < 0:
             self.check(n)
         return {"edge": float(buf[0]), "mp_layers": [float(buf[i]) for i in range(1, n)]}
+
+    # ---- multi-GPU reassembly over peer memory (nmrgnn_comm_*, see include/nmrgnn_b200.h)
+    def comm_local(self, capacity: int, world: int) -> bytes:
+        blob = C.create_string_buffer(COMM_HANDLE_BYTES)
+        self.check(self._lib.nmrgnn_comm_local(self._h, int(capacity), int(world), blob))
+        return blob.raw
+
+    def comm_init(self, rank: int, world: int, blobs: Sequence[bytes]) -> None:
+        buf = C.create_string_buffer(b"".join(blobs), COMM_HANDLE_BYTES * int(world))
+        self.check(self._lib.nmrgnn_comm_init(self._h, int(rank), int(world), buf))
+
+    def forward_sharded(self, atoms, nlist, edges, inv_degree, n_local, k, gathered, mem, stream=None):
+        self.check(self._lib.nmrgnn_forward_sharded(self._h, _ptr(atoms), _ptr(nlist), _ptr(edges), _ptr(inv_degree),
+                                                    int(n_local), int(k), _ptr(gathered), mem, stream))
+
+    def comm_buffer(self):
+        """(device pointer, capacity) of the gathered peaks [world][capacity] of the latest forward_sharded call."""
+        cap = C.c_int64(0)
+        ptr = self._lib.nmrgnn_comm_buffer(self._h, C.byref(cap))
+        return ptr, int(cap.value)
+
+    def comm_destroy(self) -> None:
+        if self._h:
+            self._lib.nmrgnn_comm_destroy(self._h)
 
     def edge_table_info(self) -> dict:
         """Create-time table of the edge block: {'active', 'intervals', 'rel_error'} (nmrgnn_edge_table_info)."""

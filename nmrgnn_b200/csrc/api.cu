@@ -19,6 +19,7 @@
 #include "kernels_tc.cuh"
 #include "knn.cuh"
 #include "edge_table.cuh"
+#include "peer_gather.cuh"
 
 using namespace nmr;
 
@@ -62,6 +63,8 @@ struct nmrgnn_handle {
   bool fast_path = false;         // F=256, H=128, E<=4: tiled kernels available
   bool force_ffma = false;
   DevBuf pos, offs;
+  std::vector<int64_t> offs_cached;     // graph_offsets currently resident in `offs` (skips the upload when unchanged:
+                                        // a frame stream repeats the same offsets, and the call stays graph-capturable)
   // tensor-core path (F=256, H=128, E<=8): pre-split, pre-swizzled operand images
   bool tc_ok = false;
   const uint8_t* edge_img = nullptr;    // [n_hidden][4][hi 8192 | lo 8192]   fp16 split
@@ -94,6 +97,16 @@ struct nmrgnn_handle {
   int edge_tab_n = 0;
   float edge_tab_finf[EDGE_TAB_MAX_E] = {0.f, 0.f, 0.f, 0.f};
   double edge_tab_err = 0.0;            // max interpolation error at interval midpoints / feature scale
+  // multi-GPU reassembly over peer memory (peer_gather.cuh)
+  int comm_rank = -1, comm_world = 0;
+  int64_t comm_capacity = 0;            // floats per (parity, rank) slot, multiple of 4
+  float* comm_gbuf = nullptr;           // local gather buffer [2][world][capacity]
+  uint32_t* comm_flags = nullptr;       // local flag words [world]
+  unsigned int* comm_done = nullptr;    // device counter of the scatter kernel
+  float* comm_peer_gbuf[PEER_MAX_WORLD] = {};
+  uint32_t* comm_peer_flags[PEER_MAX_WORLD] = {};
+  uint32_t comm_epoch = 0;
+  bool comm_ready = false;
 };
 
 namespace {
@@ -826,6 +839,24 @@ int calibrate_mp(nmrgnn_handle* h) {
   return nmrgnn_synchronize(h, nullptr);
 }
 
+void comm_release(nmrgnn_handle* h) {
+  for (int r = 0; r < h->comm_world && r < PEER_MAX_WORLD; ++r) {
+    if (r == h->comm_rank) continue;
+    if (h->comm_peer_gbuf[r]) cudaIpcCloseMemHandle(h->comm_peer_gbuf[r]);
+    if (h->comm_peer_flags[r]) cudaIpcCloseMemHandle(h->comm_peer_flags[r]);
+  }
+  for (int r = 0; r < PEER_MAX_WORLD; ++r) h->comm_peer_gbuf[r] = nullptr, h->comm_peer_flags[r] = nullptr;
+  if (h->comm_gbuf) cudaFree(h->comm_gbuf);
+  if (h->comm_flags) cudaFree(h->comm_flags);
+  if (h->comm_done) cudaFree(h->comm_done);
+  h->comm_gbuf = nullptr;
+  h->comm_flags = nullptr;
+  h->comm_done = nullptr;
+  h->comm_ready = false;
+  h->comm_world = 0;
+  h->comm_rank = -1;
+}
+
 }  // namespace
 
 // ============================================================================ C ABI
@@ -853,6 +884,7 @@ void nmrgnn_destroy(nmrgnn_handle* h) {
                     &h->tmp_out, &h->pos, &h->offs, &h->rec, &h->hmaxA, &h->hmaxB, &h->genA, &h->genB})
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  comm_release(h);
   if (h->err_flag) cudaFree(h->err_flag);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
   for (cudaEvent_t e : h->ev_copy)
@@ -1212,14 +1244,17 @@ int nmrgnn_fc_readout(nmrgnn_handle* h, const float* nodes, const float* atoms, 
   return end_call(h, stream, s);
 }
 
-int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
-                   const float* inv_degree, int64_t n_atoms, int32_t k, float* peaks, int mem, void* stream) {
+// The whole forward.  dev_peaks != NULL: the peaks stay on the device at that address (no copy to `peaks`, which may
+// be NULL); finish = false: the caller enqueues more work on the stream and ends the call itself.
+static int forward_core(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
+                        const float* inv_degree, int64_t n_atoms, int32_t k, float* peaks, int mem, void* stream,
+                        float* dev_peaks, bool finish) {
   cudaStream_t s;
   int rc = begin_call(h, mem, stream, &s);
   if (rc) return rc;
   if (n_atoms < 0 || k < 1) return fail(h, NMRGNN_ERR_BAD_DIMS, "n_atoms=%lld k=%d invalid", (long long)n_atoms, (int)k);
   if (n_atoms == 0) return NMRGNN_OK;
-  if (!atoms || !nlist || !edges || !inv_degree || !peaks) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
+  if (!atoms || !nlist || !edges || !inv_degree || (!peaks && !dev_peaks)) return fail(h, NMRGNN_ERR_BAD_DIMS, "null buffer");
   if (n_atoms >= ((int64_t)1 << 31)) return fail(h, NMRGNN_ERR_BAD_DIMS, "n_atoms exceeds int32 index range");
   PathScope scope(h, n_atoms);
   Io io{h, mem, s};
@@ -1267,7 +1302,8 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
   if ((rc = io.in(edges, n_atoms * k * sizeof(float), h->edges, &d_edges))) return rc;
   if ((rc = io.in(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;
   }
-  if ((rc = io.out_buf(peaks, n_atoms * sizeof(float), h->peaks, &d_peaks))) return rc;
+  if (dev_peaks != nullptr) d_peaks = dev_peaks;
+  else if ((rc = io.out_buf(peaks, n_atoms * sizeof(float), h->peaks, &d_peaks))) return rc;
   if ((rc = ensure(h, h->efeat, n_atoms * k * E * sizeof(float)))) return rc;
   if ((rc = ensure(h, h->hA, n_atoms * F * sizeof(float)))) return rc;
   if ((rc = ensure(h, h->hB, n_atoms * F * sizeof(float)))) return rc;
@@ -1329,8 +1365,129 @@ int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, c
   if ((rc = launch_fc(h, s, ha, (const float*)d_atoms, n_atoms, (float*)d_peaks, nullptr))) return rc;
   mark();
   h->ev_valid = h->profile;
-  if ((rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
+  if (dev_peaks == nullptr && (rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
+  if (!finish) return NMRGNN_OK;     // (copy_guard waits for the chunked uploads on the way out)
   return end_call(h, stream, s);
+}
+
+int nmrgnn_forward(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
+                   const float* inv_degree, int64_t n_atoms, int32_t k, float* peaks, int mem, void* stream) {
+  return forward_core(h, atoms, nlist, edges, inv_degree, n_atoms, k, peaks, mem, stream, nullptr, true);
+}
+
+// ---------------------------------------------------------------------------- multi-GPU (peer_gather.cuh)
+int nmrgnn_comm_local(nmrgnn_handle* h, int64_t capacity, int32_t world, void* ipc_out) {
+  if (!h || !ipc_out || world < 1 || world > PEER_MAX_WORLD || capacity < 1)
+    return fail(h, NMRGNN_ERR_BAD_DIMS, "bad arguments (world must be 1..%d)", PEER_MAX_WORLD);
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  comm_release(h);
+  h->comm_capacity = (capacity + 3) / 4 * 4;
+  h->comm_world = world;
+  const size_t gbytes = (size_t)2 * world * h->comm_capacity * sizeof(float);
+  CUDA_TRY(h, cudaMalloc(&h->comm_gbuf, gbytes));
+  CUDA_TRY(h, cudaMalloc(&h->comm_flags, PEER_MAX_WORLD * sizeof(uint32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->comm_done, sizeof(unsigned int)));
+  CUDA_TRY(h, cudaMemset(h->comm_gbuf, 0, gbytes));
+  CUDA_TRY(h, cudaMemset(h->comm_flags, 0, PEER_MAX_WORLD * sizeof(uint32_t)));
+  CUDA_TRY(h, cudaMemset(h->comm_done, 0, sizeof(unsigned int)));
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  cudaIpcMemHandle_t hb, hf;
+  std::memset(ipc_out, 0, NMRGNN_COMM_HANDLE_BYTES);
+  if (world > 1) {
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hb, h->comm_gbuf));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&hf, h->comm_flags));
+    static_assert(2 * sizeof(cudaIpcMemHandle_t) <= NMRGNN_COMM_HANDLE_BYTES, "handle blob too small");
+    std::memcpy(ipc_out, &hb, sizeof(hb));
+    std::memcpy((char*)ipc_out + sizeof(hb), &hf, sizeof(hf));
+  }
+  return NMRGNN_OK;
+}
+
+int nmrgnn_comm_init(nmrgnn_handle* h, int32_t rank, int32_t world, const void* all_ipc) {
+  if (!h || world != h->comm_world || rank < 0 || rank >= world || !h->comm_gbuf || (world > 1 && !all_ipc))
+    return fail(h, NMRGNN_ERR_BAD_DIMS, "nmrgnn_comm_init: call nmrgnn_comm_local with the same world first");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  h->comm_rank = rank;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      h->comm_peer_gbuf[r] = h->comm_gbuf;
+      h->comm_peer_flags[r] = h->comm_flags;
+      continue;
+    }
+    cudaIpcMemHandle_t hb, hf;
+    const char* blob = (const char*)all_ipc + (size_t)r * NMRGNN_COMM_HANDLE_BYTES;
+    std::memcpy(&hb, blob, sizeof(hb));
+    std::memcpy(&hf, blob + sizeof(hb), sizeof(hf));
+    void *pb = nullptr, *pf = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&pb, hb, cudaIpcMemLazyEnablePeerAccess);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(h, NMRGNN_ERR_COMM, "cannot map the gather buffer of rank %d (%s): peer access over NVLink / PCIe is "
+                  "required between the GPUs of one node", r, cudaGetErrorString(e));
+    }
+    h->comm_peer_gbuf[r] = (float*)pb;
+    h->comm_peer_flags[r] = (uint32_t*)pf;
+  }
+  h->comm_epoch = 0;
+  h->comm_ready = true;
+  return NMRGNN_OK;
+}
+
+int nmrgnn_forward_sharded(nmrgnn_handle* h, const float* atoms, const int32_t* nlist, const float* edges,
+                           const float* inv_degree, int64_t n_local, int32_t k, float* gathered, int mem, void* stream) {
+  cudaStream_t s;
+  int rc = begin_call(h, mem, stream, &s);
+  if (rc) return rc;
+  if (!h->comm_ready) return fail(h, NMRGNN_ERR_BAD_DIMS, "nmrgnn_forward_sharded: nmrgnn_comm_init has not been called");
+  if (n_local < 0 || n_local > h->comm_capacity)
+    return fail(h, NMRGNN_ERR_BAD_DIMS, "n_local=%lld exceeds the slot capacity %lld", (long long)n_local, (long long)h->comm_capacity);
+  const int world = h->comm_world, rank = h->comm_rank;
+  const uint32_t epoch = ++h->comm_epoch;
+  const int64_t cap = h->comm_capacity;
+  const int64_t parity_off = (int64_t)(epoch & 1u) * world * cap;
+  float* slot = h->comm_gbuf + parity_off + (int64_t)rank * cap;
+  // the forward writes this rank's peaks straight into its own slot of its own gather buffer
+  if (n_local > 0 &&
+      (rc = forward_core(h, atoms, nlist, edges, inv_degree, n_local, k, nullptr, mem, stream, slot, false)))
+    return rc;
+  if (world > 1) {
+    PeerArgs a{};
+    a.src = slot;
+    a.n = n_local;
+    a.world = world;
+    a.rank = rank;
+    a.slot_off = parity_off + (int64_t)rank * cap;
+    for (int r = 0; r < world; ++r) {
+      a.gbuf[r] = h->comm_peer_gbuf[r];
+      a.flags[r] = h->comm_peer_flags[r];
+    }
+    a.epoch = epoch;
+    a.done_ctr = h->comm_done;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(2 * h->num_sms, (n_local / 4 + 255) / 256));
+    peer_scatter_signal_kernel<<<blocks, 256, 0, s>>>(a);
+    peer_wait_kernel<<<1, 32, 0, s>>>(h->comm_flags, world, epoch);
+    h->launches += 2;
+  }
+  if (gathered != nullptr) {
+    const size_t bytes = (size_t)world * cap * sizeof(float);
+    CUDA_TRY(h, cudaMemcpyAsync(gathered, h->comm_gbuf + parity_off, bytes,
+                                mem == NMRGNN_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+  }
+  return end_call(h, stream, s);
+}
+
+const float* nmrgnn_comm_buffer(nmrgnn_handle* h, int64_t* capacity) {
+  if (!h || !h->comm_ready) return nullptr;
+  if (capacity) *capacity = h->comm_capacity;
+  return h->comm_gbuf + (int64_t)(h->comm_epoch & 1u) * h->comm_world * h->comm_capacity;
+}
+
+void nmrgnn_comm_destroy(nmrgnn_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  comm_release(h);
 }
 
 int nmrgnn_selftest_gemm(nmrgnn_handle* h, const float* A, const float* W, float* D, int mode) {
@@ -1482,9 +1639,18 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
   const void* d_pos;
   void *d_nl, *d_ed, *d_inv;
   if ((rc = io.in(positions, n_atoms * 3 * sizeof(float), h->pos, &d_pos))) return rc;
-  if ((rc = ensure(h, h->offs, (n_graphs + 1) * sizeof(int64_t)))) return rc;
-  // pageable host source: the runtime stages it before returning, so the caller may free it
-  CUDA_TRY(h, cudaMemcpyAsync(h->offs.p, graph_offsets, (n_graphs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  {
+    const void* before = h->offs.p;
+    if ((rc = ensure(h, h->offs, (n_graphs + 1) * sizeof(int64_t)))) return rc;
+    if (h->offs.p != before) h->offs_cached.clear();
+  }
+  if (h->offs_cached.size() != (size_t)(n_graphs + 1) ||
+      std::memcmp(h->offs_cached.data(), graph_offsets, (n_graphs + 1) * sizeof(int64_t)) != 0) {
+    // pageable host source: the runtime stages it before returning, so the caller may free it
+    h->offs_cached.assign(graph_offsets, graph_offsets + n_graphs + 1);
+    CUDA_TRY(h, cudaMemcpyAsync(h->offs.p, h->offs_cached.data(), (n_graphs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));   // different streams may use the cached copy from now on
+  }
   if ((rc = io.out_buf(nlist, n_atoms * k * sizeof(int32_t), h->nlist, &d_nl))) return rc;
   if ((rc = io.out_buf(edges, n_atoms * k * sizeof(float), h->edges, &d_ed))) return rc;
   if ((rc = io.out_buf(inv_degree, n_atoms * sizeof(float), h->invdeg, &d_inv))) return rc;

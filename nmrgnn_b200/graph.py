@@ -128,8 +128,28 @@ def read_pdb(path: str, include_hetatm: bool = True) -> Universe:
     return Universe(np.asarray(frames, np.float32), elements, names, resnames, resids)
 
 
+class UnpinnedElementWarning(UserWarning):
+    """The one-hot column of this element is not pinned against nmrdata's embedding table (third-party, absent)."""
+
+
+_PINNED = {"N", "C", "H"}          # columns 2, 3, 4: fixed by the baked peak_std / peak_avg constants of the SavedModel
+_warned: set = set()
+
+
 def one_hot_elements(elements: Iterable[str], num_elem: int = 10) -> np.ndarray:
-    idx = np.array([ELEMENT_INDEX.get(str(e).upper(), 0) for e in elements], np.int64)
+    """One-hot rows for element symbols.  Columns of N / C / H are pinned by the reference's artefact; the columns of
+    every other element follow ELEMENT_INDEX, which could not be checked against ``nmrdata.load_embeddings()`` (the
+    package is neither vendored nor installable here): the first use of such an element in a process emits an
+    ``UnpinnedElementWarning``; symbols missing from the table map to column 0 ("X") with the same warning.  In the
+    pretrained model columns 0 and 1 still hold their initial (untrained) embedding rows, columns 2-9 are trained."""
+    import warnings
+    syms = [str(e).upper() for e in elements]
+    for e in set(syms) - _PINNED - _warned:
+        _warned.add(e)
+        where = f"column {ELEMENT_INDEX[e]}" if e in ELEMENT_INDEX else "column 0 ('X': unknown element)"
+        warnings.warn(f"element {e!r} -> one-hot {where}: this assignment is not pinned against nmrdata's embedding "
+                      "table; only N, C, H are fixed by the reference's artefact", UnpinnedElementWarning, stacklevel=2)
+    idx = np.array([ELEMENT_INDEX.get(e, 0) for e in syms], np.int64)
     idx = np.where(idx < num_elem, idx, 0)
     atoms = np.zeros((len(idx), num_elem), np.float32)
     atoms[np.arange(len(idx)), idx] = 1.0

@@ -457,7 +457,8 @@ def test_eval_struct_stream(model, tmp_path):
     n = pos.shape[0]
     u = nmrgnn_b200.Universe(frames, elements, ["X%d" % i for i in range(n)], ["RES"] * n, np.arange(n) // 10)
     out_csv = str(tmp_path / "peaks.csv")
-    res = nmrgnn_b200.eval_struct(u, output_csv=out_csv, model=model)
+    res = nmrgnn_b200.eval_struct(u, output_csv=out_csv, model=model, raise_on_bad_peaks=False)
+    assert res["frames_per_batch"] == 8 and res["cuda_graph"]
     assert res["frames"] == 3 and len(res["peaks"]) == 3 * n
     with open(out_csv) as f:
         rows = list(csv.reader(f))
@@ -471,6 +472,46 @@ def test_eval_struct_stream(model, tmp_path):
     g = load_golden("g108m")
     assert np.mean(np.abs(p0 - np.round(g["peaks_f64"], 2)) <= 0.011) > 0.99
     assert all(k in res["timing"] for k in ("graph", "inference", "parsing"))
+
+
+def test_trajectory_7lgi_weak_pin_and_frame_stream(model):
+    """The reference's trajectory test (tests/test_nmrgnn.py:245-257) on its own fixture: the 10 MODELs of
+    tests/7lgi.pdb.gz (KRAS NMR ensemble, 2 770 atoms; coordinates in tests/golden/g7lgi_structure.npz) through the
+    eval-struct driver; asserts the reference's pin mean((peaks_last - peaks_first)^2) > 1, the golden peaks of the
+    traced graph for the first and the last model, and that batching the frames (FrameStream: 8 frames per launch,
+    CUDA graph) gives the same bits as one call per frame."""
+    import os
+    import nmrgnn_b200
+    from conftest import GOLDEN
+    from nmrgnn_b200.mdstream import FrameStream
+    with np.load(os.path.join(GOLDEN, "g7lgi_structure.npz")) as z:
+        frames_A = z["positions_mA"].astype(np.float32) / np.float32(1000)
+        elements = [str(e) for e in z["elements"]]
+        names, resnames, resids = z["names"], z["resnames"], z["resids"]
+        gold = {k: z[k] for k in ("peaks_first_f64", "peaks_last_f64")}
+    n = frames_A.shape[1]
+    u = nmrgnn_b200.Universe(frames_A, elements, names, resnames, resids)
+    res = nmrgnn_b200.eval_struct(u, model=model)                 # check_peaks raises on an implausible frame
+    assert res["frames"] == 10 and len(res["peaks"]) == 10 * n
+    first, last = np.array(res["peaks"][:n]), np.array(res["peaks"][-n:])
+    assert np.mean((last - first) ** 2) > 1                        # tests/test_nmrgnn.py:257
+    # golden: host-built kNN graph vs the GPU builder differ only by ties; peaks are rounded to 2 decimals in the table
+    assert np.mean(np.abs(first - np.round(gold["peaks_first_f64"], 2)) <= 0.011) > 0.99
+    assert np.mean(np.abs(last - np.round(gold["peaks_last_f64"], 2)) <= 0.011) > 0.99
+    # frame batching: same bits as frame-by-frame calls on the same path (a 2 770-atom frame alone is above tc_min_atoms)
+    fs = FrameStream(model, elements, n, 16)
+    batched = fs.run(frames_A / np.float32(10))["peaks"]
+    single = FrameStream(model, elements, n, 16, frames_per_batch=1, use_cuda_graph=False).run(frames_A[:3] / np.float32(10))["peaks"]
+    assert fs.graph_captured and batched.shape == (10, n)
+    assert np.array_equal(batched[:3], single)
+    # two "ranks" taking alternate batches cover every frame exactly once
+    fs2 = FrameStream(model, elements, n, 16, frames_per_batch=2)
+    r0, r1 = fs2.run(frames_A / np.float32(10), 0, 2), fs2.run(frames_A / np.float32(10), 1, 2)
+    both = np.empty_like(batched)
+    both[r0["frame_index"]] = r0["peaks"]
+    both[r1["frame_index"]] = r1["peaks"]
+    assert sorted(np.concatenate([r0["frame_index"], r1["frame_index"]]).tolist()) == list(range(10))
+    assert np.array_equal(both, batched)
 
 
 @pytest.mark.parametrize("hp", [
@@ -491,7 +532,7 @@ def test_generic_geometry_models(hp):
     m = nmrgnn_b200.build_GNNModel(hp, num_elem=16, seed=3)
     try:
         assert m.handle.compute_path.endswith("generic-fp32")
-        assert m.handle.edge_table_info()["active"] == (hp["fc_activation"] != "relu")
+        assert m.handle.edge_table_info()["active"] == (hp["fc_activation"] != "relu" and hp["edge_feature_size"] <= 4)
         atoms, nlist, edges, inv = workloads.ring_graph(5, 16, 2)
         y = m([atoms, nlist, edges * 0.15, inv])
         ref = orc.forward(m.params, atoms, nlist, edges * 0.15, inv, dtype=np.float64)

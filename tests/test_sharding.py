@@ -85,3 +85,57 @@ def test_sharded_forward_gloo_world2(tmp_path):
                                 reference_order=False)
     assert np.array_equal(y, ref)
     np.testing.assert_allclose(y, g["peaks"], rtol=1e-4, atol=1e-4)
+
+
+def _gpu_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import nmrgnn_b200
+        from nmrgnn_b200.sharding import ShardedModel
+        g = load_golden("prot3_batch")
+        batch = (g["atoms"], g["nlist"], g["edges"], g["inv_degree"], g["graph_offsets"])
+        m = nmrgnn_b200.load_model(device=rank)
+        m.handle.set_option("tc_min_atoms", 0)
+        sm = ShardedModel(m)                              # peer-memory reassembly (nmrgnn_forward_sharded)
+        assert sm.collective == "peer"
+        y_host = sm(batch)
+        y_host2 = sm(batch)                               # second epoch: the other parity of the gather buffers
+        dev = torch.device("cuda", rank)
+        tb = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in batch[:4]) + (batch[4],)
+        y_dev = sm(tb)                                    # device-resident in and out
+        assert y_dev.is_cuda
+        y_nccl = ShardedModel(m, collective="torch")(batch)   # comparison arm: one NCCL all-gather
+        single = m(batch[:4])
+        ok = (np.array_equal(y_host, y_host2) and np.array_equal(y_dev.cpu().numpy(), y_host)
+              and np.array_equal(y_nccl, y_host) and np.array_equal(single, y_host))
+        flag = torch.tensor([int(ok)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            np.savez(out_path, y=y_host, ok=int(flag.item()))
+        sm.close()
+        m.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_sharded_cuda_forward_two_gpus(tmp_path):
+    """World size 2 on two GPUs, NCCL process group: the CUDA forward on each rank's graphs + the peer-memory
+    reassembly equal the single-GPU forward bit for bit on both ranks (host and device inputs, two consecutive
+    epochs, and the torch.distributed all-gather arm)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "peaks.npz")
+    mp.spawn(_gpu_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    z = np.load(out)
+    g = load_golden("prot3_batch")
+    assert int(z["ok"]) == 1
+    tol = 1e-4 * np.abs(g["peaks_f64"]) + 1e-4
+    assert np.all(np.abs(z["y"] - g["peaks_f64"]) <= tol)

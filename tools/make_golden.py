@@ -79,6 +79,21 @@ def main():
                         elements=u.atoms.elements.astype("U2"), names=u.atoms.names.astype("U4"),
                         resnames=u.atoms.resnames.astype("U3"), resids=u.atoms.resids)
 
+    # 1b. the reference's trajectory fixture: KRAS NMR ensemble 7lgi.pdb.gz, 10 MODELs x 2 770 atoms
+    #     (tests/test_nmrgnn.py:245-257).  Coordinates are stored as milli-Angstrom integers (PDB precision);
+    #     golden peaks for the first and the last model on the host-built kNN-16 graph.
+    u = read_pdb(os.path.join(REF_TESTS, "7lgi.pdb.gz"))
+    frames = np.stack([(u.trajectory[i], u.atoms.positions.copy())[1] for i in range(len(u.trajectory))])
+    first = build_graph(frames[0], u.atoms.elements, 16, 10)
+    last = build_graph(frames[-1], u.atoms.elements, 16, 10)
+    p0, p0_64, _ = run(it32, it64, first, False)
+    p9, p9_64, _ = run(it32, it64, last, False)
+    np.savez_compressed(os.path.join(OUT, "g7lgi_structure.npz"), positions_mA=np.round(frames.astype(np.float64) * 1000.0).astype(np.int32),
+                        elements=u.atoms.elements.astype("U2"), names=u.atoms.names.astype("U4"),
+                        resnames=u.atoms.resnames.astype("U3"), resids=u.atoms.resids,
+                        peaks_first=p0, peaks_first_f64=p0_64, peaks_last=p9, peaks_last_f64=p9_64)
+    print("g7lgi_structure:", frames.shape, "mean((last - first)^2) =", float(np.mean((p9_64 - p0_64) ** 2)))
+
     # 2. the reference's unit-test ring graph (tests/test_nmrgnn.py:20-31), C=10, K=2
     for tag, d in (("ring5_unit", 1.0), ("ring5_bonded", 0.15)):
         a, nl, e, inv = workloads.ring_graph(5, 10, 2)
