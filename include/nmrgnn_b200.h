@@ -194,6 +194,14 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "edge_table" = 0: evaluate the edge block (RBF -> EdgeFCBlock) with the MLP kernels (tcgen05 / FFMA) for every
  *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
+ *   "mp_chain_segments" = 1 / 2 / 4 / 8: the MP layers' K loop as that many separately accumulated chains per tile, summed
+ *                  in round-to-nearest FP32 by the epilogue warps (default 1 = one 48-instruction chain; re-packs the W'
+ *                  images and recalibrates): fewer round-toward-zero steps per chain, lower error, more drains (+13 % /
+ *                  +37 % launch time at 2 / 4);
+ *   "mp_pos_comp_x100" = v: slope c' = v / 100 x 2^-24 of the MP layers' position-dependent compensation (default 50; 0
+ *                  = constant factor only; re-packs the W' images and recalibrates), see DESIGN.md "Accumulation model";
+ *   "fc_pos_comp_x100" = v / "edge_pos_comp_x100" = v: the same for the node MLP's 16-instruction chains (default 50)
+ *                  and the edge MLP's 8-instruction chains (default 30); 0 = the analytic constant factor instead;
  *   "mp_comp_x10" = c / "mp_comp_delta_x10" = d / "fc_comp_x10" = c: diagnostics (tools/diag_comp_scan.py) -- set every MP
  *                  layer's compensation to c / 10 x 2^-24 (negative: recalibrate), shift it by d / 10 x 2^-24, set the
  *                  node MLP's constant;

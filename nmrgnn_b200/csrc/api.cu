@@ -77,6 +77,12 @@ struct nmrgnn_handle {
   bool ev_valid = false;
   bool mp_tc_ok = false;                // MP layer on tensor cores (F=256, E<=3; K<=16 checked per call)
   std::vector<const uint8_t*> mp_img;   // per layer: [8 passes][E][hi 16384 | lo 16384]
+  std::vector<std::vector<float>> mp_w_host;   // originals, kept to re-pack the images when a compensation option changes
+  std::vector<std::vector<float>> edge_w_host; // the edge MLP's hidden-layer weights, likewise
+  float edge_pos_c = 0.3f;                // measured optimum for the edge MLP (profiles/r02_parity.md)
+  std::vector<std::vector<float>> fc_w_host;   // the node MLP's weights, for the same reason
+  float fc_pos_c = 0.5f;                // the same for the node MLP's 16-instruction chains (pack_fc_images)
+  float mp_pos_c = 0.5f;                // position-dependent compensation slope c' (x 2^-24), see pack_mp_images
   DevBuf rec, hmaxA, hmaxB;
   // round-toward-zero compensation of the tcgen05 accumulation (DESIGN.md "Accumulation model"):
   // multiplicative factors 1 + c applied in the epilogues
@@ -90,6 +96,7 @@ struct nmrgnn_handle {
   bool compensate = true;
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
+  int mp_nseg = 1;                      // option "mp_chain_segments": accumulation chains per MP tile (kernels_tc.cuh)
   // edge block as a create-time FP64 table of the scalar function d -> EdgeFC(RBF(d)) (edge_table.cuh)
   bool edge_table = true;               // option "edge_table"
   bool edge_tab_ok = false;             // table built and its interpolation error accepted
@@ -192,8 +199,10 @@ void pack_sw64(const float* W, int K, int ldw, int n0, int rows_valid, int rows_
 // one 64-byte swizzled row per output feature, 32 consecutive k per chunk.
 // Layout: [chunk][hi tile | lo tile], hi = fp16(w), lo = fp16((w - hi) * 2^11).
 // `get(k, n)` returns the weight for contraction index k and output feature n.
-template <typename Get>
-void pack_sw64_f16(Get get, int K, int rows_valid, int rows_tile, std::vector<uint8_t>& out) {
+// `gain(k)` (optional) is a relative weight correction g_k << 2^-11 folded into the lo image only:
+// hi = fp16(w), lo = fp16((w (1 + g_k) - hi) * 2^11) -- the position-dependent compensation of the MP layers.
+template <typename Get, typename Gain>
+void pack_sw64_f16(Get get, Gain gain, int K, int rows_valid, int rows_tile, std::vector<uint8_t>& out) {
   const int chunks = K / tc::HK;
   const size_t tile = (size_t)rows_tile * 64;
   out.assign((size_t)chunks * 2 * tile, 0);
@@ -202,11 +211,17 @@ void pack_sw64_f16(Get get, int K, int rows_valid, int rows_tile, std::vector<ui
       for (int kk = 0; kk < tc::HK; ++kk) {
         const float w = get(c * tc::HK + kk, n);
         const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn((w - __half2float(hi)) * tc::LO_SCALE);
+        const double wg = (double)w * (1.0 + gain(c * tc::HK + kk));
+        const __half lo = __float2half_rn((float)((wg - (double)__half2float(hi)) * (double)tc::LO_SCALE));
         const size_t off = (size_t)n * 64 + ((((size_t)kk >> 3) ^ (((size_t)n >> 1) & 3)) << 4) + (((size_t)kk & 7) << 1);
         std::memcpy(out.data() + (size_t)c * 2 * tile + off, &hi, 2);
         std::memcpy(out.data() + (size_t)c * 2 * tile + tile + off, &lo, 2);
       }
+}
+
+template <typename Get>
+void pack_sw64_f16(Get get, int K, int rows_valid, int rows_tile, std::vector<uint8_t>& out) {
+  pack_sw64_f16(get, [](int) { return 0.0; }, K, rows_valid, rows_tile, out);
 }
 
 // upper bound of |act(x)| for |x| <= b
@@ -653,9 +668,11 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.corr = (h->compensate && !raw) ? h->mp_corr[layer] : 1.0f;
   a.raw = raw;
   a.swz = rec_swizzled(K) ? 1 : 0;
+  a.nseg = h->mp_nseg;
   a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
-  ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+  if (a.nseg > 1) ACT_DISPATCH(a.act, mp_layer_tc_seg_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+  else ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   h->launches++;
   return NMRGNN_OK;
 }
@@ -741,6 +758,84 @@ int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float*
 // protein-like graph is pushed through the exact-FP32 FFMA kernels; at every layer the raw
 // contraction D is computed by both paths on identical inputs and c = -<D_tc - D_ffma, D_ffma>_w /
 // <D_ffma, D_ffma>_w, weighted by the squared activation slope.  The epilogue then multiplies by 1 + c.
+// (Re)builds the MP layers' W' operand images.  Contraction index kg = (pass*E + n)*32 + ll  <->  input feature
+// 32*pass + ll, edge channel n; one tcgen05 instruction covers 16 consecutive kg.
+// Position-dependent compensation: the accumulator is truncated toward zero once per instruction, so a product that
+// enters at instruction k of an n-instruction chain is shrunk n - k times more than the last one; to first order the
+// expected loss of the chain is c' * sum_k (n - k + 1) P_k (P_k: the instruction's exact sum; measured c' = 0.5 x 2^-24,
+// tools/sim_tc_accum.py) -- a LINEAR functional of the products, unlike the truncation itself.  It is folded into the
+// weights: w_k (1 + c' (n - k + 1)); the factor is far below fp16 resolution, so only the lo image changes and the run
+// time is untouched.  What a constant factor cannot follow (partial sums that overshoot the result) this does.
+int pack_mp_images(nmrgnn_handle* h) {
+  const int F = h->d.atom_features, E = h->d.edge_features, L = h->d.n_mp;
+  const int n_instr = F * E / 16, chain = n_instr / h->mp_nseg;
+  const double cpos = h->compensate ? (double)h->mp_pos_c / 16777216.0 : 0.0;
+  const bool fresh = h->mp_img.empty();
+  if (fresh) h->mp_img.assign(L, nullptr);
+  std::vector<uint8_t> img;
+  for (int l = 0; l < L; ++l) {
+    const float* src = h->mp_w_host[l].data();   // w[l_in, m, n]
+    pack_sw64_f16(
+        [&](int kg, int m) {
+          const int qch = kg / 32, ll = kg % 32, ps = qch / E, n = qch % E;
+          return src[((size_t)(32 * ps + ll) * F + m) * E + n];
+        },
+        [&](int kg) { return cpos * (double)(chain - (kg / 16) % chain); }, F * E, F, F, img);
+    if (fresh) {
+      if (int rc = upload_bytes(h, img.data(), img.size(), &h->mp_img[l])) return rc;
+    } else {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->mp_img[l]), img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  return NMRGNN_OK;
+}
+
+// (Re)builds the edge MLP's hidden-layer operand images [layer][4 chunks][hi 8192 | lo 8192] with the position-dependent
+// compensation of their H/16-instruction chains (see pack_mp_images).
+int pack_edge_images(nmrgnn_handle* h) {
+  const int H = h->d.edge_hidden, n_instr = H / 16;
+  const double cpos = h->compensate ? (double)h->edge_pos_c / 16777216.0 : 0.0;
+  std::vector<uint8_t> img, all;
+  for (const auto& Wv : h->edge_w_host) {
+    const float* W = Wv.data();
+    pack_sw64_f16([&](int k, int n) { return W[(size_t)k * H + n]; }, [&](int k) { return cpos * (double)(n_instr - k / 16); },
+                  H, H, H, img);
+    all.insert(all.end(), img.begin(), img.end());
+  }
+  if (!h->edge_img) return upload_bytes(h, all.data(), all.size(), &h->edge_img);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->edge_img), all.data(), all.size(), cudaMemcpyHostToDevice));
+  return NMRGNN_OK;
+}
+
+// (Re)builds the node MLP's operand images: per layer [8 chunks][2 halves][hi 8192 | lo 8192] (last layer: one half),
+// with the position-dependent compensation of its 16-instruction chains in the lo images (see pack_mp_images).
+int pack_fc_images(nmrgnn_handle* h) {
+  const int F = h->d.atom_features, n_fc = h->d.n_fc;
+  const int n_instr = F / 16;
+  const double cpos = h->compensate ? (double)h->fc_pos_c / 16777216.0 : 0.0;
+  std::vector<uint8_t> all;
+  for (int i = 0; i < n_fc; ++i) {
+    const bool last = (i == n_fc - 1);
+    const int outw = last ? F / 2 : F;
+    const float* W = h->fc_w_host[i].data();
+    // pack each 128-column half as its own 8-chunk image, then interleave
+    std::vector<uint8_t> half_img[2];
+    const int halves = last ? 1 : 2;
+    for (int hf = 0; hf < halves; ++hf)
+      pack_sw64_f16([&](int k, int n) { return W[(size_t)k * outw + hf * 128 + n]; },
+                    [&](int k) { return cpos * (double)(n_instr - k / 16); }, F, 128, 128, half_img[hf]);
+    for (int c = 0; c < 8; ++c)
+      for (int hf = 0; hf < halves; ++hf)
+        all.insert(all.end(), half_img[hf].begin() + (size_t)c * 16384, half_img[hf].begin() + (size_t)(c + 1) * 16384);
+  }
+  if (!h->fc_img) return upload_bytes(h, all.data(), all.size(), &h->fc_img);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->fc_img), all.data(), all.size(), cudaMemcpyHostToDevice));
+  return NMRGNN_OK;
+}
+
 int calibrate_mp(nmrgnn_handle* h) {
   const int N = 2048, K = 16;
   const int C = h->d.num_elem, F = h->d.atom_features, E = h->d.edge_features;
@@ -829,9 +924,10 @@ int calibrate_mp(nmrgnn_handle* h) {
       num += w * ((double)dt[i] - r) * r;
       den += w * r * r;
     }
+    // (the residual after the position-dependent part of the W' images; it may have either sign)
     double c = den > 0.0 ? -num / den : 0.0;
-    if (!(c > 0.0)) c = 0.0;                 // also catches NaN
-    if (c > 256.0 / 16777216.0) c = 256.0 / 16777216.0;
+    if (!(c == c)) c = 0.0;                  // NaN
+    c = std::fmin(std::fmax(c, -256.0 / 16777216.0), 256.0 / 16777216.0);
     h->mp_corr[l] = (float)(1.0 + c);
     std::swap(ha, hb);
   }
@@ -1018,7 +1114,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
   h->tc_ok = h->fast_path && E <= 4 && dims->n_edge_fc >= 2;
   if (h->tc_ok) {
     const int n_hidden = dims->n_edge_fc - 1;
-    std::vector<uint8_t> img, all;
+    std::vector<uint8_t> img;
     std::vector<float> bias((size_t)n_hidden * 128);
     int wi = 0;
     float bound = 1.0f;  // RBF * mask <= 1
@@ -1026,21 +1122,17 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     for (int l = 0; l < n_hidden; ++l, wi += 2) {
       const float* W = weights[wi];
       if (max_abs(W, (size_t)H * H) > 60000.f) h->tc_ok = false;
-      pack_sw64_f16([&](int k, int n) { return W[(size_t)k * H + n]; }, H, H, H, img);
-      all.insert(all.end(), img.begin(), img.end());
+      h->edge_w_host.emplace_back(W, W + (size_t)H * H);
       std::memcpy(bias.data() + (size_t)l * 128, weights[wi + 1], 128 * sizeof(float));
       bound = act_bound(bound * max_col_abs_sum(W, H, H) + max_abs(weights[wi + 1], H), dims->fc_activation);
       const int sx = scale_exp_for(bound);
       h->edge_in_scale[l + 1] = tc::pow2f_exact(-sx);
       h->edge_out_scale[l + 1] = tc::pow2f_exact(sx);
     }
-    // round-toward-zero compensation for an H-long chain (H/16 MMA instructions), folded into the
-    // scale that the epilogue applies to the accumulator anyway
-    // (measured on the pretrained net: the 4-layer softplus chain shrinks by 5.9 x 2^-24 in total, half of
-    //  what the exchangeable-increment model 0.36 (n + 1) predicts per layer; profiles/r01_tc_accuracy.md)
-    h->edge_rz = 1.0f + 0.17f * (float)(H / 16 + 1) / 16777216.0f;
-    for (int l = 0; l <= n_hidden; ++l) h->edge_out_scale[l] *= h->edge_rz;
-    TRY_RC(upload_bytes(h, all.data(), all.size(), &h->edge_img));
+    // round-toward-zero compensation of the H/16-instruction chains: position-dependent, in the lo images
+    // (pack_edge_images); edge_rz is the constant alternative (option "edge_pos_comp_x100" = 0), folded into the scale
+    // that the epilogue applies to the accumulator anyway
+    TRY_RC(pack_edge_images(h));
     {
       const float* W = weights[wi];
       if (max_abs(W, (size_t)H * E) > 60000.f) h->tc_ok = false;
@@ -1061,25 +1153,20 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
   }
   if (h->mp_tc_ok) {
     const int w0 = 2 * dims->n_edge_fc + 1;
-    h->mp_img.resize(dims->n_mp);
-    std::vector<uint8_t> img;
-    for (int l = 0; l < dims->n_mp; ++l) {
-      const float* src = weights[w0 + l];   // w[l_in, m, n]
-      // contraction index kg = (pass*E + n)*32 + ll  <->  input feature 32*pass + ll, edge channel n
-      pack_sw64_f16(
-          [&](int kg, int m) {
-            const int qch = kg / 32, ll = kg % 32, ps = qch / E, n = qch % E;
-            return src[((size_t)(32 * ps + ll) * F + m) * E + n];
-          },
-          F * E, F, F, img);
-      TRY_RC(upload_bytes(h, img.data(), img.size(), &h->mp_img[l]));
-    }
+    h->mp_w_host.resize(dims->n_mp);
+    for (int l = 0; l < dims->n_mp; ++l) h->mp_w_host[l].assign(weights[w0 + l], weights[w0 + l] + (size_t)F * F * E);
+    TRY_RC(pack_mp_images(h));
     ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
+    ACT_SET_SMEM(mp_layer_tc_seg_kernel, MTC_SMEM);
     // 196 KB of shared memory, 60 KB of L1 for the gathers (see MTC_SMEM)
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_seg_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_seg_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_seg_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_seg_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     h->mp_corr.assign(dims->n_mp, 1.0f);
     TRY_RC(calibrate_mp(h));
     h->launches = 0;
@@ -1094,23 +1181,16 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
   }
   if (h->fc_tc_ok) {
     const int w0 = 2 * dims->n_edge_fc + 1 + dims->n_mp;
-    std::vector<uint8_t> all, img;
     std::vector<float> bias((size_t)dims->n_fc * 256, 0.f);
     float gain = 1.0f, offs = 0.0f;
+    h->fc_w_host.resize(dims->n_fc);
     for (int i = 0; i < dims->n_fc; ++i) {
       const bool last = (i == dims->n_fc - 1);
       const int outw = last ? F2 : F;
       const float* W = weights[w0 + 2 * i];
       const float* b = weights[w0 + 2 * i + 1];
       std::memcpy(bias.data() + (size_t)i * 256, b, outw * sizeof(float));
-      // [chunk][half][hi | lo]: pack each 128-column half as its own 8-chunk image, then interleave
-      std::vector<uint8_t> half_img[2];
-      const int halves = last ? 1 : 2;
-      for (int hf = 0; hf < halves; ++hf)
-        pack_sw64_f16([&](int k, int n) { return W[(size_t)k * outw + hf * 128 + n]; }, F, 128, 128, half_img[hf]);
-      for (int c = 0; c < 8; ++c)
-        for (int hf = 0; hf < halves; ++hf)
-          all.insert(all.end(), half_img[hf].begin() + (size_t)c * 16384, half_img[hf].begin() + (size_t)(c + 1) * 16384);
+      h->fc_w_host[i].assign(W, W + (size_t)F * outw);
       // |x_l| <= gain * max|x_0| + offs  (input of layer i), then through act(x W + b) + x
       h->fc_gain[i] = gain;
       h->fc_offs[i] = offs;
@@ -1123,9 +1203,9 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
         gain = gain * (ws + 1.0f);
       }
     }
-    TRY_RC(upload_bytes(h, all.data(), all.size(), &h->fc_img));
+    TRY_RC(pack_fc_images(h));
     TRY_RC(upload(h, bias.data(), bias.size(), &h->fc_bias));
-    h->fc_rz = 1.0f + 0.17f * (float)(F / 16 + 1) / 16777216.0f;
+    h->fc_rz = 1.0f;
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
   }
   update_path(h);
@@ -1598,6 +1678,44 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
     h->fc_rz = 1.0f + (float)value / 10.0f / 16777216.0f;
     return NMRGNN_OK;
   }
+  if (std::strcmp(name, "mp_chain_segments") == 0) {
+    if (value != 1 && value != 2 && value != 4 && value != 8) return fail(h, NMRGNN_ERR_BAD_DIMS, "mp_chain_segments must be 1, 2, 4 or 8");
+    if (value != h->mp_nseg) {
+      h->mp_nseg = value;
+      if (h->mp_tc_ok) {                             // the compensation belongs to a chain length
+        if (int rc = pack_mp_images(h)) return rc;
+        return calibrate_mp(h);
+      }
+    }
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "edge_pos_comp_x100") == 0) {  // the same for the edge MLP (H/16-instruction chains)
+    if (value < 0 || value > 400) return fail(h, NMRGNN_ERR_BAD_DIMS, "edge_pos_comp_x100 must be in 0..400");
+    if (!h->tc_ok) return NMRGNN_OK;
+    const int n_hidden = h->d.n_edge_fc - 1;
+    const float rz = value ? 1.0f : 1.0f + 0.17f * (float)(h->d.edge_hidden / 16 + 1) / 16777216.0f;
+    if (h->compensate)
+      for (int l = 0; l <= n_hidden; ++l) h->edge_out_scale[l] = h->edge_out_scale[l] / h->edge_rz * rz;
+    h->edge_rz = rz;
+    h->edge_pos_c = (float)value / 100.0f;
+    return pack_edge_images(h);
+  }
+  if (std::strcmp(name, "fc_pos_comp_x100") == 0) {  // the same for the node MLP (16-instruction chains)
+    if (value < 0 || value > 400) return fail(h, NMRGNN_ERR_BAD_DIMS, "fc_pos_comp_x100 must be in 0..400");
+    h->fc_pos_c = (float)value / 100.0f;
+    // without the position-dependent part: the analytic constant of a linear trajectory
+    h->fc_rz = value ? 1.0f : 1.0f + 0.17f * (float)(h->d.atom_features / 16 + 1) / 16777216.0f;
+    return h->fc_tc_ok ? pack_fc_images(h) : NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_pos_comp_x100") == 0) {  // position-dependent compensation slope c' = value / 100 x 2^-24
+    if (value < 0 || value > 400) return fail(h, NMRGNN_ERR_BAD_DIMS, "mp_pos_comp_x100 must be in 0..400");
+    h->mp_pos_c = (float)value / 100.0f;
+    if (h->mp_tc_ok) {
+      if (int rc = pack_mp_images(h)) return rc;
+      return calibrate_mp(h);
+    }
+    return NMRGNN_OK;
+  }
   if (std::strcmp(name, "tc_min_atoms") == 0) {
     h->tc_min_atoms = value < 0 ? 0 : value;
     return NMRGNN_OK;
@@ -1608,7 +1726,13 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
       for (int l = 0; l <= n_hidden; ++l) h->edge_out_scale[l] = value ? h->edge_out_scale[l] * h->edge_rz
                                                                        : h->edge_out_scale[l] / h->edge_rz;
     }
+    const bool changed = h->compensate != (value != 0);
     h->compensate = value != 0;
+    if (changed && h->tc_ok)                                 // the position-dependent part lives in the operand images
+      if (int rc = pack_edge_images(h)) return rc;
+    if (changed && h->fc_tc_ok)
+      if (int rc = pack_fc_images(h)) return rc;
+    if (changed && h->mp_tc_ok) return pack_mp_images(h);
     return NMRGNN_OK;
   }
   return fail(h, NMRGNN_ERR_BAD_DIMS, "unknown option '%s'", name);

@@ -898,9 +898,17 @@ struct MpTcArgs {
   float corr;                // 1 + c: compensates the round-toward-zero accumulation of tcgen05
   int raw;                   // 1: h_out = inv_degree * D (no activation, no residual) -- calibration tap
   int swz;                   // records are slot-swizzled (rec_slot; K = 8 or 16)
+  int nseg;                  // accumulation-chain segments per tile: 1, 2, 4 or 8 (see "chain segments" below)
   long long* dbg;            // optional [gridDim][8] cycle counters (diagnostics): see tools/diag_mp_roles.py
 };
 
+// Chain segments.  tcgen05 accumulates round-toward-zero; over the 48 instructions of the main product that is a
+// trajectory-dependent error (it adds up coherently while a partial sum stays on one side of zero) which no constant
+// factor removes, and it is the largest error source of the tensor-core path (profiles/r02_parity.md).  With nseg > 1 the
+// K loop is cut into nseg chains of 8 / nseg feature passes: after each chain the epilogue warps (idle during a tile
+// anyway) drain main + corr, apply the chain's compensation and add the partial sums in round-to-nearest FP32 -- the
+// running sum is parked in the tile's own rows of h_out (written and re-read by the same thread; L2-resident) -- and
+// the next chain starts from a cleared accumulator.  The producers keep filling the operand ring during a drain.
 constexpr int MTC_THREADS = 512;
 constexpr int MTC_PASSES = 8;          // 256 / 32
 constexpr int MTC_BRING = 4;           // W' ring: slots of 16 KB, the hi and the lo image of a (pass, n) chunk are separate slots
@@ -923,7 +931,7 @@ constexpr int MTC_PAIR_BSLOT = 16384;
 constexpr int MTC_PAIR_ASTAGES = 3;    // the halved W' ring pays for a third operand stage: the two CTAs of a pair decouple
 constexpr size_t MTC_PAIR_SMEM = 512 + MTC_PAIR_ASTAGES * 3 * 16384 + MTC_PAIR_BRING * MTC_PAIR_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 
-template <int ACT, bool PAIR>
+template <int ACT, bool PAIR, bool SEG>
 __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   constexpr int BRING = PAIR ? MTC_PAIR_BRING : MTC_BRING;
   constexpr int BSLOT = PAIR ? MTC_PAIR_BSLOT : MTC_BSLOT;
@@ -935,7 +943,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   uint8_t* b_ring = a_st + AST * 3 * 16384;                 // [BRING][hi 16384 | lo 16384]
   float4* rec_s = reinterpret_cast<float4*>(b_ring + BRING * BSLOT);       // [128 * K]
   float* fscale = reinterpret_cast<float*>(rec_s + 128 * MTC_KMAX);        // [2][128]  2^-s
-  float* oscale = fscale + 2 * 128;                                         // [2][128]  2^s * inv_degree * corr
+  float* oscale = fscale + 2 * 128;                                         // [2][128]  2^s * inv_degree
   uint64_t* bars = reinterpret_cast<uint64_t*>(oscale + 2 * 128);
   uint64_t* a_full = bars;            // [2]
   uint64_t* a_empty = a_full + AST;   // [AST]
@@ -1051,16 +1059,19 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_f16(PAIR ? 256 : 128, 256);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
-      uint32_t it = 0, pass = 0, t = 0;
+      uint32_t it = 0, pass = 0, t = 0, dph = 0;
+      const int seg_passes = MTC_PASSES / p.nseg;
       long long w_d = 0, w_a = 0, w_b = 0, c0 = 0;
       const long long k0 = clock64();
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
-        if (p.dbg) c0 = clock64();
-        if (PAIR) tc::mbar_wait_cluster(d_empty, (t & 1) ^ 1);   // both epilogues have drained their accumulators
-        else tc::mbar_wait(d_empty, (t & 1) ^ 1);  // epilogue has drained the previous tile's accumulators
-        if (p.dbg) w_d += clock64() - c0;
-        tc::tc_fence_after();
         for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
+          if (ps % seg_passes == 0) {            // a new accumulation chain: the epilogue has drained the previous one
+            if (p.dbg) c0 = clock64();
+            if (PAIR) tc::mbar_wait_cluster(d_empty, (dph & 1) ^ 1);
+            else tc::mbar_wait(d_empty, (dph & 1) ^ 1);
+            if (p.dbg) w_d += clock64() - c0;
+            tc::tc_fence_after();
+          }
           const uint32_t st = pass % AST;
           if (p.dbg) c0 = clock64();
           if (PAIR) tc::mbar_wait_cluster(&a_full[st], (pass / AST) & 1);
@@ -1082,13 +1093,15 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
-              const uint32_t acc = (ps | n | ks) != 0;
+              // main restarts with every chain; the correction accumulator (its truncation is scaled by 2^-11)
+              // runs through the whole tile and is read once, by the last chain's epilogue
+              const uint32_t acc = ((ps % seg_passes) | n | ks) != 0, acc_c = (ps | n | ks) != 0;
               if (PAIR) {
                 tc::umma_f16_pair(d_main, ah + adv, bh + adv, idesc, acc);
-                tc::umma_f16_pair(d_corr, al + adv, bh + adv, idesc, acc);
+                tc::umma_f16_pair(d_corr, al + adv, bh + adv, idesc, acc_c);
               } else {
                 tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
-                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc_c);
               }
             }
             uint64_t bl;
@@ -1116,9 +1129,12 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           }
           if (PAIR) tc::umma_commit_pair(&a_empty[st], 3);
           else tc::umma_commit(&a_empty[st]);
+          if ((ps + 1) % seg_passes == 0) {      // chain complete: hand the accumulators to the epilogue
+            if (PAIR) tc::umma_commit_pair(d_full, 3);
+            else tc::umma_commit(d_full);
+            ++dph;
+          }
         }
-        if (PAIR) tc::umma_commit_pair(d_full, 3);
-        else tc::umma_commit(d_full);
       }
       if (p.dbg) {
         long long* o = p.dbg + (size_t)blockIdx.x * 8;
@@ -1140,80 +1156,195 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     const int grow = q * 32 + (lane & 24);         // first row of the group
     const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_corr = t_main + 256u;
-    uint32_t t = 0;
+    uint32_t t = 0, dph = 0;
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
       const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));   // 0: the pair's trailing empty tile
       tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
-      const float osc = oscale[(t & 1) * 128 + row];
-      // rows grow .. grow+7 of this group, clamped for the loads (stores are predicated)
-      const float* hin = p.h_in + (rows > 0 ? a0 + min(grow, rows - 1) : 0) * 256 + gi * 4;
-      float* hout = p.h_out + (a0 + grow) * 256 + gi * 4;
-      // (rows past the end of a partial tile re-read the tile's last row; their stores are predicated off)
-      const int rlast = rows > 0 ? rows - 1 - min(grow, rows - 1) : 0;
-      float4 res[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) res[k] = p.raw ? make_float4(0.f, 0.f, 0.f, 0.f) : tc::ldg128(hin + min(k, rlast) * 256);
-      tc::mbar_wait(d_full, t & 1);
-      const long long e0 = p.dbg ? clock64() : 0;
-      tc::tc_fence_after();
       float hm[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) hm[k] = 0.0f;
+      if constexpr (!SEG) {
+        // one accumulation chain per tile (the default): drain, compensate, activate, add the residual
+        const float osc = oscale[(t & 1) * 128 + row] * p.corr;   // (1 + c) once per row: one chain
+        // rows grow .. grow+7 of this group, clamped for the loads (stores are predicated)
+        const float* hin = p.h_in + (rows > 0 ? a0 + min(grow, rows - 1) : 0) * 256 + gi * 4;
+        float* hout = p.h_out + (a0 + grow) * 256 + gi * 4;
+        // (rows past the end of a partial tile re-read the tile's last row; their stores are predicated off)
+        const int rlast = rows > 0 ? rows - 1 - min(grow, rows - 1) : 0;
+        float4 res[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) res[k] = p.raw ? make_float4(0.f, 0.f, 0.f, 0.f) : tc::ldg128(hin + min(k, rlast) * 256);
+        tc::mbar_wait(d_full, dph & 1);
+        ++dph;
+        const long long e0 = p.dbg ? clock64() : 0;
+        tc::tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        float4 x[8];
-        {
-          float v[16];
-          tc::tmem_ld16_combined(t_main + cc * 32, t_corr + cc * 32, v);
+        for (int cc = 0; cc < 8; ++cc) {
+          float4 x[8];
+          {
+            float v[16];
+            tc::tmem_ld16_combined(t_main + cc * 32, t_corr + cc * 32, v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
-          tc::tmem_ld16_combined(t_main + cc * 32 + 16, t_corr + cc * 32 + 16, v);
+            for (int j = 0; j < 4; ++j) x[j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
+            tc::tmem_ld16_combined(t_main + cc * 32 + 16, t_corr + cc * 32 + 16, v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[4 + j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
-        }
-        // 8 x 8 transpose of float4 inside the 8-lane group (3 butterfly stages)
+            for (int j = 0; j < 4; ++j) x[4 + j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
+          }
+          // 8 x 8 transpose of float4 inside the 8-lane group (3 butterfly stages)
 #pragma unroll
-        for (int m = 1; m < 8; m <<= 1) {
-          const bool up = (lane & m) != 0;
+          for (int m = 1; m < 8; m <<= 1) {
+            const bool up = (lane & m) != 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (j & m) continue;
-            const float4 lo4 = x[j], hi4 = x[j | m];
-            float4 snd = up ? lo4 : hi4, rcv;
-            rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m);
-            rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
-            rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m);
-            rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
-            x[j] = up ? rcv : lo4;
-            x[j | m] = up ? hi4 : rcv;
+            for (int j = 0; j < 8; ++j) {
+              if (j & m) continue;
+              const float4 lo4 = x[j], hi4 = x[j | m];
+              float4 snd = up ? lo4 : hi4, rcv;
+              rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m);
+              rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
+              rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m);
+              rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
+              x[j] = up ? rcv : lo4;
+              x[j | m] = up ? hi4 : rcv;
+            }
+          }
+          // now x[k] = columns cc*32 + gi*4 .. +3 of row grow + k
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float4 o;
+            if (p.raw) {
+              o = x[k];
+            } else {
+              o.x = act_t<ACT>(x[k].x) + res[k].x;
+              o.y = act_t<ACT>(x[k].y) + res[k].y;
+              o.z = act_t<ACT>(x[k].z) + res[k].z;
+              o.w = act_t<ACT>(x[k].w) + res[k].w;
+            }
+            hm[k] = fmaxf(hm[k], fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+            if (grow + k < rows) *reinterpret_cast<float4*>(hout + k * 256 + cc * 32) = o;
+            // the residual of the next 32 columns is in flight during the next accumulator read + transposition
+            if (cc + 1 < 8 && !p.raw) res[k] = tc::ldg128(hin + min(k, rlast) * 256 + (cc + 1) * 32);
           }
         }
-        // now x[k] = columns cc*32 + gi*4 .. +3 of row grow + k
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) tc::mbar_arrive_cluster(d_empty_ldr);
+          else tc::mbar_arrive(d_empty);
+        }
+        if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
+      } else {
+        const float* oscr = oscale + (t & 1) * 128 + grow;   // 2^s * inv_degree of rows grow .. grow+7 (the rows this thread finishes)
+        // rows grow .. grow+7 of this group, clamped for the loads (stores are predicated)
+        const float* hin = p.h_in + (rows > 0 ? a0 + min(grow, rows - 1) : 0) * 256 + gi * 4;
+        float* hout = p.h_out + (a0 + grow) * 256 + gi * 4;
+        // the same rows clamped like `hin`, for re-reading the running sum of a partial tile's trailing groups
+        const float* hpart = p.h_out + (rows > 0 ? a0 + min(grow, rows - 1) : 0) * 256 + gi * 4;
+        // (rows past the end of a partial tile re-read the tile's last row; their stores are predicated off)
+        const int rlast = rows > 0 ? rows - 1 - min(grow, rows - 1) : 0;
+        float4 buf[8];                  // in flight: partial sums of the previous chains, then the residual rows
+        const float cf = p.corr;        // chain compensation, applied per segment (oscale carries 2^s * inv_degree only)
+        for (int seg = 0; seg < p.nseg; ++seg, ++dph) {
+          const bool first = seg == 0, last = seg == p.nseg - 1;
+          if (!first) {                 // running sum of the previous chains, columns 0..31: this thread wrote it
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          float4 o;
-          if (p.raw) {
-            o = x[k];
-          } else {
-            o.x = act_t<ACT>(x[k].x) + res[k].x;
-            o.y = act_t<ACT>(x[k].y) + res[k].y;
-            o.z = act_t<ACT>(x[k].z) + res[k].z;
-            o.w = act_t<ACT>(x[k].w) + res[k].w;
+            for (int k = 0; k < 8; ++k) buf[k] = *reinterpret_cast<const float4*>(hpart + min(k, rlast) * 256);
           }
-          hm[k] = fmaxf(hm[k], fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-          if (grow + k < rows) *reinterpret_cast<float4*>(hout + k * 256 + cc * 32) = o;
-          // the residual of the next 32 columns is in flight during the next accumulator read + transposition
-          if (cc + 1 < 8 && !p.raw) res[k] = tc::ldg128(hin + min(k, rlast) * 256 + (cc + 1) * 32);
+          tc::mbar_wait(d_full, dph & 1);
+          const long long e0 = p.dbg ? clock64() : 0;
+          tc::tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < 8; ++cc) {
+            float4 x[8];
+            {
+              float v[16];
+              if (last) tc::tmem_ld16_combined(t_main + cc * 32, t_corr + cc * 32, v);
+              else tc::tmem_ld16(t_main + cc * 32, v);             // the correction accumulator keeps running
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] = make_float4(v[4 * j] * cf, v[4 * j + 1] * cf, v[4 * j + 2] * cf, v[4 * j + 3] * cf);
+              if (last) tc::tmem_ld16_combined(t_main + cc * 32 + 16, t_corr + cc * 32 + 16, v);
+              else tc::tmem_ld16(t_main + cc * 32 + 16, v);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[4 + j] = make_float4(v[4 * j] * cf, v[4 * j + 1] * cf, v[4 * j + 2] * cf, v[4 * j + 3] * cf);
+            }
+            // 8 x 8 transpose of float4 inside the 8-lane group (3 butterfly stages)
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) {
+              const bool up = (lane & m) != 0;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j & m) continue;
+                const float4 lo4 = x[j], hi4 = x[j | m];
+                float4 snd = up ? lo4 : hi4, rcv;
+                rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, m);
+                rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, m);
+                rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, m);
+                rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, m);
+                x[j] = up ? rcv : lo4;
+                x[j | m] = up ? hi4 : rcv;
+              }
+            }
+            // now x[k] = columns cc*32 + gi*4 .. +3 of row grow + k (accumulator units, this chain only)
+            if (!first) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                x[k].x += buf[k].x;
+                x[k].y += buf[k].y;
+                x[k].z += buf[k].z;
+                x[k].w += buf[k].w;
+              }
+            }
+            if (!last) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (grow + k < rows) *reinterpret_cast<float4*>(hout + k * 256 + cc * 32) = x[k];
+            } else {
+              // the residual rows travel while the activation is evaluated
+              if (!p.raw) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) buf[k] = tc::ldg128(hin + min(k, rlast) * 256 + cc * 32);
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float osk = oscr[k];
+                x[k].x *= osk;
+                x[k].y *= osk;
+                x[k].z *= osk;
+                x[k].w *= osk;
+                if (!p.raw) {
+                  x[k].x = act_t<ACT>(x[k].x);
+                  x[k].y = act_t<ACT>(x[k].y);
+                  x[k].z = act_t<ACT>(x[k].z);
+                  x[k].w = act_t<ACT>(x[k].w);
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float4 o = x[k];
+                if (!p.raw) {
+                  o.x += buf[k].x;
+                  o.y += buf[k].y;
+                  o.z += buf[k].z;
+                  o.w += buf[k].w;
+                }
+                hm[k] = fmaxf(hm[k], fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                if (grow + k < rows) *reinterpret_cast<float4*>(hout + k * 256 + cc * 32) = o;
+              }
+            }
+            if (!first && cc + 1 < 8) {   // the running sum of the next 32 columns, in flight during the next accumulator read
+#pragma unroll
+              for (int k = 0; k < 8; ++k) buf[k] = *reinterpret_cast<const float4*>(hpart + min(k, rlast) * 256 + (cc + 1) * 32);
+            }
+          }
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR) tc::mbar_arrive_cluster(d_empty_ldr);
+            else tc::mbar_arrive(d_empty);
+          }
+          if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
         }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (PAIR) tc::mbar_arrive_cluster(d_empty_ldr);
-        else tc::mbar_arrive(d_empty);
-      }
-      if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
       // row maxima: reduce over the 8 lanes of the group, lane k writes row grow + k
       float mine = 0.0f;
 #pragma unroll
@@ -1320,7 +1451,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           s = b > 0.0f ? max(s, 0) : 0;
           s = min(s, 100);
           fs[row] = tc::pow2f_exact(-s);
-          os[row] = row < rows ? tc::pow2f_exact(s) * p.inv_degree[a0 + row] * p.corr : 0.0f;
+          os[row] = row < rows ? tc::pow2f_exact(s) * p.inv_degree[a0 + row] : 0.0f;
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1396,7 +1527,12 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
 
 template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
-  mp_layer_tc_body<ACT, false>(p);
+  mp_layer_tc_body<ACT, false, false>(p);
+}
+// the same with the K loop cut into p.nseg accumulation chains (option "mp_chain_segments" > 1)
+template <int ACT>
+__global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_seg_kernel(const MpTcArgs p) {
+  mp_layer_tc_body<ACT, false, true>(p);
 }
 
 }  // namespace nmr

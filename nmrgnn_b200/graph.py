@@ -136,7 +136,7 @@ _PINNED = {"N", "C", "H"}          # columns 2, 3, 4: fixed by the baked peak_st
 _warned: set = set()
 
 
-def one_hot_elements(elements: Iterable[str], num_elem: int = 10) -> np.ndarray:
+def one_hot_elements(elements: Iterable[str], num_elem: int = 10, warn: bool = True) -> np.ndarray:
     """One-hot rows for element symbols.  Columns of N / C / H are pinned by the reference's artefact; the columns of
     every other element follow ELEMENT_INDEX, which could not be checked against ``nmrdata.load_embeddings()`` (the
     package is neither vendored nor installable here): the first use of such an element in a process emits an
@@ -144,7 +144,7 @@ def one_hot_elements(elements: Iterable[str], num_elem: int = 10) -> np.ndarray:
     pretrained model columns 0 and 1 still hold their initial (untrained) embedding rows, columns 2-9 are trained."""
     import warnings
     syms = [str(e).upper() for e in elements]
-    for e in set(syms) - _PINNED - _warned:
+    for e in (set(syms) - _PINNED - _warned) if warn else ():
         _warned.add(e)
         where = f"column {ELEMENT_INDEX[e]}" if e in ELEMENT_INDEX else "column 0 ('X': unknown element)"
         warnings.warn(f"element {e!r} -> one-hot {where}: this assignment is not pinned against nmrdata's embedding "

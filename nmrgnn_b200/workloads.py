@@ -100,7 +100,7 @@ def protein_graph(seed: int, n_lo: int = 2000, n_hi: int = 3000, neighbor_number
         pad = rng.random(nlist.shape) < pad_fraction
         nlist[pad] = 0
         edges[pad] = 0.0
-    atoms = one_hot_elements(_elements(rng, n, _PROTEIN_ELEMENTS), num_elem)
+    atoms = one_hot_elements(_elements(rng, n, _PROTEIN_ELEMENTS), num_elem, warn=False)
     return atoms, nlist, edges, inv_degree_from_nlist(nlist)
 
 
@@ -114,7 +114,7 @@ def small_molecule_graph(seed: int, n_lo: int = 20, n_hi: int = 60, neighbor_num
     pad = rng.random(nlist.shape) < pad_fraction
     nlist[pad] = 0
     edges[pad] = 0.0
-    atoms = one_hot_elements(_elements(rng, n, _SMALL_ELEMENTS), num_elem)
+    atoms = one_hot_elements(_elements(rng, n, _SMALL_ELEMENTS), num_elem, warn=False)
     return atoms, nlist, edges, inv_degree_from_nlist(nlist)
 
 

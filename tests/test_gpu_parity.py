@@ -372,12 +372,11 @@ def config2_batch():
 
 def test_config2_full_size_against_golden(model, config2_batch):
     """Every one of the 164 105 atoms of the bench workload against the fp64 execution of the reference's traced
-    graph.  Tolerance 1e-4 relative + 1e-4 ppm, no budget factors:
-      * exact-FP32 kernels: every atom within the tolerance (measured max 0.43);
-      * tensor-core path: 99.99 % of the atoms within HALF the tolerance, and at every level of the error
-        distribution at least as close to the exact result as the reference's own float32 arithmetic (the traced
-        graph executed in float32 misses the tolerance on 5 of these atoms, worst 2.05: C / N atoms whose peak sits
-        ~120 ppm below the element mean, where full*std + avg cancels); measured max 1.38, 2 atoms above 1."""
+    graph.  Tolerance 1e-4 relative + 1e-4 ppm, no budget factors, EVERY atom, on all three compute paths (measured
+    max: exact-FP32 kernels 0.43, tensor-core path 0.58).  For scale: the traced graph executed in float32 misses the
+    tolerance on 5 of these atoms, worst 2.05 (C / N atoms whose peak sits ~120 ppm below the element mean, where
+    full*std + avg cancels); the tensor-core path must also be at least as close to the exact result as that float32
+    execution at every level of the error distribution."""
     ref64, ref32 = _full_fixture("full_config2", config2_batch)
     atoms, nlist, edges, inv, offs = config2_batch
     assert model.handle.compute_path == "edge-table-f64+tcgen05-fp16x3(mp,fc)"
@@ -388,13 +387,11 @@ def test_config2_full_size_against_golden(model, config2_batch):
         assert np.array_equal(y == 0, ref64 == 0), name                 # elements without statistics: exactly 0
     e = {k: _err(v, ref64) for k, v in ys.items()}
     print({k: (round(float(v.max()), 3), int((v > 1).sum()), round(float(np.quantile(v, 0.9999)), 3)) for k, v in e.items()})
-    assert e["ffma"].max() <= 1.0
-    for name in ("tc", "tc-mlp"):
+    for name in ("ffma", "tc", "tc-mlp"):
+        assert e[name].max() <= 1.0, name
         assert np.quantile(e[name], 0.9999) <= 0.5, name
-        assert e[name].max() <= e32.max() and (e[name] > 1).sum() <= (e32 > 1).sum(), name
         for q in (0.5, 0.99, 0.999, 0.9999):
             assert np.quantile(e[name], q) <= max(np.quantile(e32, q), 0.02), (name, q)
-    assert e["tc"].max() <= 1.5 and (e["tc"] > 1).sum() <= 2
 
 
 def test_config2_full_size_properties(model, config2_batch):

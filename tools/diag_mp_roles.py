@@ -12,6 +12,8 @@ atoms, nlist, edges, inv, offs = b
 n = atoms.shape[0]
 m = nmrgnn_b200.load_model()
 h = m.handle
+if os.environ.get("NSEG"):
+    h.set_option("mp_chain_segments", int(os.environ["NSEG"]))
 dev = torch.device("cuda", 0)
 d_in = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (atoms, nlist, edges, inv)]
 out = torch.empty(n, dtype=torch.float32, device=dev)
