@@ -17,6 +17,7 @@
 #include "kernels_ffma.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_mp_nsplit.cuh"
 #include "knn.cuh"
 #include "edge_table.cuh"
 #include "peer_gather.cuh"
@@ -96,6 +97,7 @@ struct nmrgnn_handle {
   bool compensate = true;
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
+  bool mp_nsplit = false;               // option "mp_nsplit": MP layers by column-split CTA pairs (kernels_mp_nsplit.cuh)
   int mp_nseg = 1;                      // option "mp_chain_segments": accumulation chains per MP tile (kernels_tc.cuh)
   // edge block as a create-time FP64 table of the scalar function d -> EdgeFC(RBF(d)) (edge_table.cuh)
   bool edge_table = true;               // option "edge_table"
@@ -649,9 +651,13 @@ int launch_pack_rec(nmrgnn_handle* h, cudaStream_t s, const int32_t* nlist, cons
   return NMRGNN_OK;
 }
 
+// hmax_in: one row maximum per atom, or (in_pair) two partial maxima per atom as the column-split kernel writes them.
+// Returns in *out_pair (optional) which of the two forms hmax_out has.
+inline bool in_pair_unsupported(const nmrgnn_handle* h) { return h->num_sms < 2; }
+
 int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in, const float* hmax_in,
                  const float4* rec, const float* invdeg, int64_t n, int K, float* h_out, float* hmax_out,
-                 int raw = 0) {
+                 int raw = 0, int in_pair = 0, int* out_pair = nullptr) {
   if (n == 0) return NMRGNN_OK;
   MpTcArgs a{};
   a.h_in = h_in;
@@ -669,9 +675,15 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.raw = raw;
   a.swz = rec_swizzled(K) ? 1 : 0;
   a.nseg = h->mp_nseg;
+  a.hmax_pair = in_pair;
   a.dbg = h->mp_dbg;
   const int64_t tiles = (n + 127) / 128;
-  if (a.nseg > 1) ACT_DISPATCH(a.act, mp_layer_tc_seg_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+  const bool nsplit = h->mp_nsplit && a.nseg == 1 && !in_pair_unsupported(h);
+  if (out_pair) *out_pair = nsplit ? 1 : 0;
+  if (nsplit) {
+    const int64_t pairs = std::min<int64_t>(tiles, h->num_sms / 2);
+    ACT_DISPATCH(a.act, mp_layer_np_kernel, (unsigned)(2 * pairs), MNP_THREADS, MNP_SMEM, s, a);
+  } else if (a.nseg > 1) ACT_DISPATCH(a.act, mp_layer_tc_seg_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   else ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   h->launches++;
   return NMRGNN_OK;
@@ -878,8 +890,8 @@ int calibrate_mp(nmrgnn_handle* h) {
   if ((rc = ensure(h, h->hB, (size_t)N * F * 4))) return rc;
   if ((rc = ensure(h, h->tmp_in, (size_t)N * F * 4))) return rc;
   if ((rc = ensure(h, h->tmp_out, (size_t)N * F * 4))) return rc;
-  if ((rc = ensure(h, h->hmaxA, (size_t)N * 4))) return rc;
-  if ((rc = ensure(h, h->hmaxB, (size_t)N * 4))) return rc;
+  if ((rc = ensure(h, h->hmaxA, (size_t)N * 8))) return rc;
+  if ((rc = ensure(h, h->hmaxB, (size_t)N * 8))) return rc;
   CUDA_TRY(h, cudaMemcpyAsync(h->atoms.p, atoms.data(), atoms.size() * 4, cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(h->nlist.p, nl.data(), nl.size() * 4, cudaMemcpyHostToDevice, s));
   CUDA_TRY(h, cudaMemcpyAsync(h->edges.p, edges.data(), edges.size() * 4, cudaMemcpyHostToDevice, s));
@@ -1158,6 +1170,12 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(pack_mp_images(h));
     ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
     ACT_SET_SMEM(mp_layer_tc_seg_kernel, MTC_SMEM);
+    ACT_SET_SMEM(mp_layer_np_kernel, MNP_SMEM);
+    // 162 KB of shared memory: the 164 KB configuration leaves 92 KB of L1 for the gathers
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
     // 196 KB of shared memory, 60 KB of L1 for the gathers (see MTC_SMEM)
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
@@ -1287,8 +1305,8 @@ int nmrgnn_mp_layer(nmrgnn_handle* h, int32_t layer, const float* nodes_in, cons
   if ((rc = io.out_buf(nodes_out, n_atoms * F * sizeof(float), h->hB, &d_out))) return rc;
   if (mp_tc_usable(h, k)) {
     if ((rc = ensure(h, h->rec, n_atoms * k * sizeof(float4)))) return rc;
-    if ((rc = ensure(h, h->hmaxA, n_atoms * sizeof(float)))) return rc;
-    if ((rc = ensure(h, h->hmaxB, n_atoms * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->hmaxA, 2 * n_atoms * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->hmaxB, 2 * n_atoms * sizeof(float)))) return rc;
     if ((rc = launch_pack_rec(h, s, (const int32_t*)d_nl, (const float*)d_ef, (float4*)h->rec.p, n_atoms * k, n_atoms, k)))
       return rc;
     if ((rc = launch_absmax(h, s, (const float*)d_in, n_atoms, (float*)h->hmaxA.p))) return rc;
@@ -1403,8 +1421,8 @@ static int forward_core(nmrgnn_handle* h, const float* atoms, const int32_t* nli
   if (mp_tc_usable(h, k) && h->d.n_mp > 0) {
     // tensor-core route: the edge kernel emits {e0,e1,e2,idx} records, the MP layers carry max|h| per atom
     if ((rc = ensure(h, h->rec, n_atoms * k * sizeof(float4)))) return rc;
-    if ((rc = ensure(h, h->hmaxA, n_atoms * sizeof(float)))) return rc;
-    if ((rc = ensure(h, h->hmaxB, n_atoms * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->hmaxA, 2 * n_atoms * sizeof(float)))) return rc;
+    if ((rc = ensure(h, h->hmaxB, 2 * n_atoms * sizeof(float)))) return rc;
     float4* rec = (float4*)h->rec.p;
     float* ma = (float*)h->hmaxA.p;
     float* mb = (float*)h->hmaxB.p;
@@ -1419,8 +1437,9 @@ static int forward_core(nmrgnn_handle* h, const float* atoms, const int32_t* nli
     if (n_chunks > 1) CUDA_TRY(h, cudaStreamWaitEvent(s, h->ev_copy[8], 0));
     if ((rc = launch_embed(h, s, (const float*)d_atoms, n_atoms, ha, ma))) return rc;
     mark();
+    int m_pair = 0;
     for (int l = 0; l < h->d.n_mp; ++l) {
-      if ((rc = launch_mp_tc(h, s, l, ha, ma, rec, (const float*)d_inv, n_atoms, k, hb, mb))) return rc;
+      if ((rc = launch_mp_tc(h, s, l, ha, ma, rec, (const float*)d_inv, n_atoms, k, hb, mb, 0, m_pair, &m_pair))) return rc;
       mark();
       std::swap(ha, hb);
       std::swap(ma, mb);
@@ -1654,8 +1673,8 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
         }
       if (n)
         printf("mp roles (mean cycles per CTA over %d CTAs): mma total %.0f | mma waits: epilogue %.0f producers %.0f W' %.0f | "
-               "epilogue busy %.0f | producer waits: a_empty %.0f rec %.0f\n",
-               n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[5] / n, m[6] / n);
+               "epilogue busy %.0f | producer waits: a_empty %.0f rec %.0f | shipper idle %.0f\n",
+               n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[5] / n, m[6] / n, m[7] / n);
     }
     if (value == 0) h->mp_dbg = nullptr;
     return NMRGNN_OK;
@@ -1676,6 +1695,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "fc_comp_x10") == 0) {        // diagnostics: node-MLP compensation = value / 10 x 2^-24
     h->fc_rz = 1.0f + (float)value / 10.0f / 16777216.0f;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_nsplit") == 0) {
+    h->mp_nsplit = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_chain_segments") == 0) {

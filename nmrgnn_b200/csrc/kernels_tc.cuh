@@ -899,6 +899,7 @@ struct MpTcArgs {
   int raw;                   // 1: h_out = inv_degree * D (no activation, no residual) -- calibration tap
   int swz;                   // records are slot-swizzled (rec_slot; K = 8 or 16)
   int nseg;                  // accumulation-chain segments per tile: 1, 2, 4 or 8 (see "chain segments" below)
+  int hmax_pair;             // hmax_in holds two partial row maxima per atom (written by the column-split kernel)
   long long* dbg;            // optional [gridDim][8] cycle counters (diagnostics): see tools/diag_mp_roles.py
 };
 

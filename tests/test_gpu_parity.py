@@ -394,6 +394,25 @@ def test_config2_full_size_against_golden(model, config2_batch):
             assert np.quantile(e[name], q) <= max(np.quantile(e32, q), 0.02), (name, q)
 
 
+def test_column_split_pair_kernel_is_bit_identical(model, config2_batch):
+    """Option mp_nsplit: the MP layers on column-split CTA pairs (cluster of 2, operand halves shipped through
+    distributed shared memory, double-buffered accumulators) give the same bits as the one-CTA kernel -- on the full
+    bench batch (even / odd tile counts per cluster, partial last tile), a single graph, and K = 8 small molecules."""
+    from nmrgnn_b200 import workloads
+    from nmrgnn_b200.workloads import take_graphs
+    atoms, nlist, edges, inv, offs = config2_batch
+    small = workloads.small_molecule_batch(64, first_seed=5)
+    cases = [(atoms, nlist, edges, inv), take_graphs(config2_batch, np.array([7]))[:4], small[:4]]
+    ref = [model(g) for g in cases]
+    try:
+        model.handle.set_option("mp_nsplit", 1)
+        got = [model(g) for g in cases]
+    finally:
+        model.handle.set_option("mp_nsplit", 0)
+    for a, b in zip(ref, got):
+        assert np.array_equal(a, b)
+
+
 def test_config2_full_size_properties(model, config2_batch):
     from nmrgnn_b200.workloads import take_graphs
     atoms, nlist, edges, inv, offs = config2_batch

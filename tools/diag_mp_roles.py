@@ -12,6 +12,8 @@ atoms, nlist, edges, inv, offs = b
 n = atoms.shape[0]
 m = nmrgnn_b200.load_model()
 h = m.handle
+if os.environ.get("NSPLIT"):
+    h.set_option("mp_nsplit", int(os.environ["NSPLIT"]))
 if os.environ.get("NSEG"):
     h.set_option("mp_chain_segments", int(os.environ["NSEG"]))
 dev = torch.device("cuda", 0)
