@@ -1172,10 +1172,10 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     ACT_SET_SMEM(mp_layer_tc_seg_kernel, MTC_SMEM);
     ACT_SET_SMEM(mp_layer_np_kernel, MNP_SMEM);
     // 162 KB of shared memory: the 164 KB configuration leaves 92 KB of L1 for the gathers
-    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
-    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
-    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
-    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 71));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     // 196 KB of shared memory, 60 KB of L1 for the gathers (see MTC_SMEM)
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));

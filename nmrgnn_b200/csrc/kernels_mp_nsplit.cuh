@@ -22,13 +22,13 @@
 namespace nmr {
 
 constexpr int MNP_THREADS = 512;
-constexpr int MNP_AST = 2;             // operand stages: [3 chunks][hi 8192 | lo 8192] for 128 rows
-constexpr int MNP_BRING = 6;           // W' ring: 8 KB slots = this CTA's 128 N rows of one image (hi or lo) of a (pass, n) chunk
+constexpr int MNP_AST = 3;             // operand stages: [3 chunks][hi 8192 | lo 8192] for 128 rows
+constexpr int MNP_BRING = 4;           // W' ring: 8 KB slots = this CTA's 128 N rows of one image (hi or lo) of a (pass, n) chunk
 constexpr int MNP_BSLOT = 8192;
 // 64-byte-swizzled tiles need a 512-byte aligned base.  162 KB: the SM can run in its 164 KB configuration (92 KB of L1
 // for the gathers).
 constexpr size_t MNP_SMEM = 512 + MNP_AST * 3 * 16384 + MNP_BRING * MNP_BSLOT + 64 * MTC_KMAX * 16 + 2 * (64 + 128) * 4 + 256;
-static_assert(MNP_SMEM + 1024 <= 164 * 1024, "column-split MP kernel no longer fits the 164 KB shared-memory configuration");
+static_assert(MNP_SMEM + 1024 <= 196 * 1024, "column-split MP kernel no longer fits the 196 KB shared-memory configuration");
 
 namespace tc {
 // bulk async copy from this CTA's shared memory into the shared memory of a CTA of the cluster; the bytes are counted

@@ -154,12 +154,42 @@ class GNNParams:
     @classmethod
     def from_tf_checkpoint(cls, path: str, peak_std: Optional[np.ndarray] = None,
                            peak_avg: Optional[np.ndarray] = None, edge_fc_layers: Optional[int] = None,
-                           rbf_low: float = 0.005, rbf_high: float = 0.20,
-                           mp_activation: str = "softplus", fc_activation: str = "softplus") -> "GNNParams":
+                           rbf_low: Optional[float] = None, rbf_high: Optional[float] = None,
+                           mp_activation: Optional[str] = None, fc_activation: Optional[str] = None) -> "GNNParams":
         """Build from a TensorBundle written by the reference (``model.save`` /
         ``ModelCheckpoint``; nmrgnn/main.py:63-68,82).  ``variables/<i>`` are the
         model's sub-layer weights in creation order: edge FC (kernel,bias)*, MP w*,
-        FC (kernel,bias)* — the split is recovered from tensor ranks/shapes."""
+        FC (kernel,bias)* — the split is recovered from tensor ranks/shapes.
+
+        What the weights do not say — activations, RBF range, per-element standards — is taken, in this order, from
+        the keyword arguments, from the SavedModel's ``saved_model.pb`` (Keras layer metadata and the constants baked
+        into the traced graph, as ``tf.keras.models.load_model`` restores them; savedmodel_meta.py), or, for the
+        standards of a bare ``ModelCheckpoint`` only, from the packaged standards (the reference builds the model
+        with ``nmrdata.load_standards()`` before ``load_weights``, nmrgnn/model.py:222-228).  Activations and RBF
+        range of a bare checkpoint must be given: the reference needs the same ``hp`` to rebuild the model, and a
+        silent default would predict wrong values for a relu / tanh model."""
+        from .savedmodel_meta import read_savedmodel_meta, standards_from_constants
+        meta = None
+        for d in (path, os.path.dirname(os.path.normpath(path))):
+            if os.path.isfile(os.path.join(d, "saved_model.pb")):
+                meta = read_savedmodel_meta(d)
+                break
+        hp = (meta or {}).get("hypers") or {}
+        rbf = (meta or {}).get("rbf") or {}
+        if mp_activation is None:
+            mp_activation = hp.get("mp_activation")
+        if fc_activation is None:
+            fc_activation = hp.get("fc_activation")
+        if rbf_low is None:
+            rbf_low = rbf.get("low", hp.get("rbf_low"))
+        if rbf_high is None:
+            rbf_high = rbf.get("high", hp.get("rbf_high"))
+        missing = [k for k, v in (("mp_activation", mp_activation), ("fc_activation", fc_activation),
+                                  ("rbf_low", rbf_low), ("rbf_high", rbf_high)) if v is None]
+        if missing:
+            raise ValueError(f"{path}: {', '.join(missing)} cannot be recovered "
+                             f"({'saved_model.pb has no Keras metadata for them' if meta else 'no saved_model.pb next to the checkpoint'}); "
+                             "pass them as keyword arguments (the hyper-parameters the model was trained with)")
         from .tensorbundle import load_gnn_variables
 
         v = load_gnn_variables(path)
@@ -178,13 +208,22 @@ class GNNParams:
         if edge_fc_layers is not None and len(edge_fc) != edge_fc_layers:
             raise ValueError("edge_fc_layers mismatch")
         C = v["embed_layer/kernel"].shape[0]
+        if (peak_std is None or peak_avg is None) and meta is not None:
+            baked = standards_from_constants(meta["constants"], C)
+            if baked is None:
+                raise ValueError(f"{path}: the per-element standards baked into the traced graph (gnn-model/mul_3/y, "
+                                 "mul_4/y) were not found; pass peak_std / peak_avg")
+            peak_std, peak_avg = baked
         if peak_std is None or peak_avg is None:
             peak_std, peak_avg = baseline_standards(C)
+        if rbf.get("count") is not None and int(rbf["count"]) != edge_fc[0][0].shape[0]:
+            raise ValueError("RBFExpansion count in saved_model.pb does not match the first edge layer's input width")
         p = cls(edge_fc=edge_fc, embed=v["embed_layer/kernel"], mp_w=seq[first:last + 1], fc=fc,
                 out=(v["out_layer/kernel"], v["out_layer/bias"]),
                 peak_std=np.asarray(peak_std, np.float32), peak_avg=np.asarray(peak_avg, np.float32),
-                rbf_low=rbf_low, rbf_high=rbf_high, mp_activation=mp_activation,
-                fc_activation=fc_activation, meta={"source": os.path.basename(os.path.normpath(path))})
+                rbf_low=float(rbf_low), rbf_high=float(rbf_high), mp_activation=str(mp_activation),
+                fc_activation=str(fc_activation), meta={"source": os.path.basename(os.path.normpath(path)),
+                                                        "hypers_from": "saved_model.pb" if hp or rbf else "arguments"})
         p.validate()
         return p
 

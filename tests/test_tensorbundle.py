@@ -75,7 +75,11 @@ def test_roundtrip_synthetic_bundle(tmp_path):
         tensors[f"variables/{i}/.OPTIMIZER_SLOT/optimizer/m" + suffix] = np.zeros_like(a)
     os.makedirs(tmp_path / "variables")
     _write_bundle(str(tmp_path / "variables" / "variables"), tensors)
-    q = GNNParams.from_tf_checkpoint(str(tmp_path), peak_std=p.peak_std, peak_avg=p.peak_avg)
+    # a bare checkpoint does not say which activations / RBF range the model was trained with: no silent defaults
+    with pytest.raises(ValueError, match="mp_activation"):
+        GNNParams.from_tf_checkpoint(str(tmp_path), peak_std=p.peak_std, peak_avg=p.peak_avg)
+    q = GNNParams.from_tf_checkpoint(str(tmp_path), peak_std=p.peak_std, peak_avg=p.peak_avg, mp_activation="softplus",
+                                     fc_activation="softplus", rbf_low=0.005, rbf_high=0.2)
     assert len(q.edge_fc) == 3 and len(q.mp_w) == 2 and len(q.fc) == 3
     for (a, b), (c, d) in zip(p.edge_fc + p.fc, q.edge_fc + q.fc):
         assert np.array_equal(a, c) and np.array_equal(b, d)
@@ -83,6 +87,59 @@ def test_roundtrip_synthetic_bundle(tmp_path):
         assert np.array_equal(a, c)
     v = tbm.load_gnn_variables(str(tmp_path), verify_crc=True)
     assert "optimizer/iter" not in v
+
+
+def _pb(field, payload, wt=2):
+    """one protobuf field: length-delimited bytes (wt 2) or varint (wt 0)"""
+    def varint(x):
+        out = bytearray()
+        while True:
+            b = x & 0x7F
+            x >>= 7
+            out.append(b | (0x80 if x else 0))
+            if not x:
+                return bytes(out)
+    if wt == 0:
+        return varint(field << 3) + varint(payload)
+    return varint((field << 3) | 2) + varint(len(payload)) + payload
+
+
+def test_savedmodel_metadata_overrides_defaults(tmp_path):
+    """A reference-trained SavedModel with relu / tanh, another RBF range and other standards loads with exactly
+    those (the loader used to assume softplus / 0.005-0.20 / the baseline standards)."""
+    import json
+    p = GNNParams.random(num_elem=7, atom_feature_size=32, edge_feature_size=2, edge_hidden_size=16, mp_layers=2,
+                         fc_layers=3, edge_fc_layers=3, seed=4)
+    suffix = "/.ATTRIBUTES/VARIABLE_VALUE"
+    tensors = {"out_layer/kernel" + suffix: p.out[0], "out_layer/bias" + suffix: p.out[1],
+               "embed_layer/kernel" + suffix: p.embed}
+    seq = [a for Wb in p.edge_fc for a in Wb] + list(p.mp_w) + [a for Wb in p.fc for a in Wb]
+    for i, a in enumerate(seq):
+        tensors[f"variables/{i}" + suffix] = a
+    os.makedirs(tmp_path / "variables")
+    _write_bundle(str(tmp_path / "variables" / "variables"), tensors)
+    hyp = {"class_name": "HyperParameters", "config": {"space": [], "values": {
+        "mp_activation": "tanh", "fc_activation": "relu", "rbf_low": 0.01, "rbf_high": 0.3}}}
+    metas = [{"class_name": "MPBlock", "name": "mp-block", "config": {"name": "mp-block", "hypers": hyp}},
+             {"class_name": "RBFExpansion", "name": "rbf-layer", "config": {"low": 0.01, "high": 0.3, "count": 16}}]
+    nodes = b"".join(_pb(1, _pb(4, _pb(1, b"_tf_keras_layer") + _pb(3, json.dumps(m).encode()))) for m in metas)
+    std = np.arange(1, 8, dtype=np.float32)
+    avg = np.arange(7, dtype=np.float32) * 10
+
+    def const(name, arr):
+        tensor = _pb(1, 1, 0) + _pb(2, _pb(2, _pb(1, arr.size, 0))) + _pb(4, arr.astype("<f4").tobytes())
+        attr = _pb(1, b"value") + _pb(2, _pb(8, tensor))
+        return _pb(3, _pb(1, name.encode()) + _pb(2, b"Const") + _pb(5, attr))
+    fn = _pb(1, const("gnn-model/mul_3/y", std) + const("gnn-model/mul_4/y", avg))
+    meta_graph = _pb(2, _pb(2, fn)) + _pb(7, nodes)
+    (tmp_path / "saved_model.pb").write_bytes(_pb(1, 1, 0) + _pb(2, meta_graph))
+    q = GNNParams.from_tf_checkpoint(str(tmp_path))
+    assert (q.mp_activation, q.fc_activation, q.rbf_low, q.rbf_high) == ("tanh", "relu", 0.01, 0.3)
+    assert np.array_equal(q.peak_std, std) and np.array_equal(q.peak_avg, avg)
+    assert q.meta["hypers_from"] == "saved_model.pb"
+    # explicit arguments still win
+    q = GNNParams.from_tf_checkpoint(str(tmp_path), mp_activation="softplus")
+    assert q.mp_activation == "softplus" and q.fc_activation == "relu"
 
 
 def test_bad_magic(tmp_path):
@@ -102,8 +159,10 @@ def test_reference_bundle_matches_survey_table_and_export():
         assert e.shape == shape and e.offset == off and e.dtype == 1
     v = tbm.load_gnn_variables(REF, verify_crc=True)
     assert sum(a.size for a in v.values()) == 1070477
-    p = GNNParams.from_tf_checkpoint(REF)
+    p = GNNParams.from_tf_checkpoint(REF)          # hypers and standards from the reference's saved_model.pb
     q = GNNParams.load(baseline_path())
+    assert (p.mp_activation, p.fc_activation, p.rbf_low, p.rbf_high) == ("softplus", "softplus", 0.005, 0.2)
+    assert np.array_equal(p.peak_std, q.peak_std) and np.array_equal(p.peak_avg, q.peak_avg)
     assert np.array_equal(p.mp_w[2], q.mp_w[2]) and np.array_equal(p.out[1], q.out[1])
     assert np.array_equal(p.edge_fc[0][0], q.edge_fc[0][0]) and np.array_equal(p.fc[3][0], q.fc[3][0])
 
