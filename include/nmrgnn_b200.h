@@ -21,7 +21,10 @@
  *     (device buffers only); errors detected on the device (out-of-range
  *     neighbour index) are then reported by nmrgnn_synchronize();
  *   - a handle may be used by one host thread at a time; different handles
- *     (e.g. one per GPU) are independent.
+ *     (e.g. one per GPU) are independent.  The per-call workspaces belong to the
+ *     handle, so its calls execute one after the other: a call on a stream other
+ *     than the one of the previous asynchronous call first waits (on the device)
+ *     for that call to finish;
  *   - all tensors are dense row-major; float = IEEE binary32; nlist = int32.
  */
 #ifndef NMRGNN_B200_H

@@ -42,6 +42,11 @@ struct nmrgnn_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // host-buffer calls: H2D of later chunks overlaps the edge kernel of earlier ones
   cudaEvent_t ev_copy[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // The workspaces below belong to the handle: calls must be stream-ordered.  An asynchronous call leaves an event
+  // behind; a call on another stream waits for it before touching the workspaces (begin_call / end_call).
+  cudaEvent_t ev_last = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool last_async = false;
   std::string err;
   std::string path = "ffma";
   int64_t launches = 0;
@@ -324,12 +329,27 @@ int begin_call(nmrgnn_handle* h, int mem, void* stream, cudaStream_t* s) {
     return fail(h, NMRGNN_ERR_BAD_DIMS, "host buffers require stream == NULL (synchronous call)");
   CUDA_TRY(h, cudaSetDevice(h->device));
   *s = stream ? (cudaStream_t)stream : h->stream;
+  if (h->last_async && h->last_stream != *s) {   // the previous call may still be using the workspaces on its stream
+    CUDA_TRY(h, cudaStreamWaitEvent(*s, h->ev_last, 0));
+    h->last_async = false;
+  }
   return NMRGNN_OK;
 }
 
 int end_call(nmrgnn_handle* h, void* stream, cudaStream_t s) {
   CUDA_TRY(h, cudaGetLastError());
-  if (stream != nullptr) return NMRGNN_OK;  // asynchronous: caller synchronises
+  if (stream != nullptr) {                  // asynchronous: caller synchronises
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(h, cudaStreamIsCapturing(s, &cap));
+    if (cap == cudaStreamCaptureStatusNone) {
+      if (!h->ev_last) CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
+      CUDA_TRY(h, cudaEventRecord(h->ev_last, s));
+      h->last_stream = s;
+      h->last_async = true;
+    }
+    return NMRGNN_OK;
+  }
+  h->last_async = false;
   return nmrgnn_synchronize(h, nullptr);
 }
 
@@ -992,6 +1012,7 @@ void nmrgnn_destroy(nmrgnn_handle* h) {
                     &h->tmp_out, &h->pos, &h->offs, &h->rec, &h->hmaxA, &h->hmaxB, &h->genA, &h->genB})
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
+  if (h->ev_last) cudaEventDestroy(h->ev_last);
   comm_release(h);
   if (h->err_flag) cudaFree(h->err_flag);
   if (h->err_flag_host) cudaFreeHost(h->err_flag_host);
@@ -1313,9 +1334,18 @@ int nmrgnn_mp_layer(nmrgnn_handle* h, int32_t layer, const float* nodes_in, cons
     if ((rc = launch_mp_tc(h, s, layer, (const float*)d_in, (const float*)h->hmaxA.p, (const float4*)h->rec.p,
                            (const float*)d_inv, n_atoms, k, (float*)d_out, (float*)h->hmaxB.p)))
       return rc;
-  } else if ((rc = launch_mp(h, s, layer, (const float*)d_in, (const int32_t*)d_nl, (const float*)d_ef,
-                             (const float*)d_inv, n_atoms, k, (float*)d_out)))
-    return rc;
+  } else {
+    // the exact-FP32 / generic MP kernels clamp a neighbour index instead of flagging it (in the whole forward the edge
+    // stage does the check); TF's GatherV2 raises, and so must this entry point on every route
+    if (n_atoms > 0) {
+      gen_index_check_kernel<<<(unsigned)((n_atoms * k + 255) / 256), 256, 0, s>>>((const int32_t*)d_nl, n_atoms * k, n_atoms,
+                                                                                  h->err_flag);
+      h->launches++;
+    }
+    if ((rc = launch_mp(h, s, layer, (const float*)d_in, (const int32_t*)d_nl, (const float*)d_ef,
+                        (const float*)d_inv, n_atoms, k, (float*)d_out)))
+      return rc;
+  }
   if ((rc = io.finish(nodes_out, d_out, n_atoms * F * sizeof(float)))) return rc;
   return end_call(h, stream, s);
 }

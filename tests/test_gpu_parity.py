@@ -136,6 +136,29 @@ def test_reference_unit_test_shapes(model):
     assert set(nmrgnn_b200.custom_objects) >= {"MPLayer", "RBFExpansion", "EdgeFCBlock", "MPBlock", "FCBlock"}
 
 
+def test_calls_on_different_streams_are_serialised(model):
+    """The workspaces belong to the handle: an asynchronous device-tensor call on one stream followed immediately by a
+    call on another stream (or by a host-buffer call) must not overwrite them while the first is still running."""
+    import torch
+    from nmrgnn_b200 import workloads
+    a = workloads.protein_batch(8, first_seed=3)[:4]
+    b = workloads.protein_batch(8, first_seed=40)[:4]
+    ya, yb = model(a), model(b)
+    dev = torch.device("cuda", model.device)
+    ta = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in a)
+    tb = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in b)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize(dev)
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            oa = model(ta)
+        with torch.cuda.stream(s2):
+            ob = model(tb)
+        yh = model(a)                                   # host-buffer call on the handle's own stream right behind them
+        torch.cuda.synchronize(dev)
+        assert np.array_equal(oa.cpu().numpy(), ya) and np.array_equal(ob.cpu().numpy(), yb) and np.array_equal(yh, ya)
+
+
 def test_device_tensors_equal_host_path(model):
     import torch
     g = load_golden("prot300")
@@ -229,6 +252,17 @@ def test_errors(model):
         model((atoms, bad, edges, inv))
     y = model((atoms, nlist, edges, inv))                     # handle still usable afterwards
     assert tol_ratio(y, g["peaks_f64"]) <= 1.0
+    # the per-block MP layer raises too, on the exact-FP32 route (small call) and on the tensor-core route
+    bad[0, 0] = 5
+    for tc_min in (1024, 0):
+        model.handle.set_option("tc_min_atoms", tc_min)
+        try:
+            with pytest.raises(IndexError):
+                model.mp_block.mp[0]([g["embed"], bad, g["edge_features"], inv])
+            out = model.mp_block.mp[0]([g["embed"], nlist, g["edge_features"], inv])
+            assert out.shape == g["embed"].shape
+        finally:
+            model.handle.set_option("tc_min_atoms", 1024)
     with pytest.raises(ValueError):
         model((atoms[:, :5], nlist, edges, inv))
     with pytest.raises(ValueError):
