@@ -197,6 +197,8 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "edge_table" = 0: evaluate the edge block (RBF -> EdgeFCBlock) with the MLP kernels (tcgen05 / FFMA) for every
  *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
+ *   "knn_cells" = 0: nmrgnn_knn_graph searches every atom of the graph per query (brute force) instead of the cell list
+ *                  (default 1; identical output);
  *   "mp_nsplit" = 1: run the MP layers on column-split CTA pairs (kernels_mp_nsplit.cuh: two CTAs of a cluster share one
  *                  128-atom tile, each owns 128 output columns and gathers 64 rows; double-buffered accumulators) --
  *                  bit-identical results, measured slower than the one-CTA kernel (0.45 vs 0.37 ms); default 0;

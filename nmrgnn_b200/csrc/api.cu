@@ -68,7 +68,8 @@ struct nmrgnn_handle {
   int* err_flag_host = nullptr;   // pinned
   bool fast_path = false;         // F=256, H=128, E<=4: tiled kernels available
   bool force_ffma = false;
-  DevBuf pos, offs;
+  DevBuf pos, offs, knn_sorted, knn_cells, knn_grid;   // kNN builder: positions, offsets, cell-list workspaces
+  bool knn_cells_on = true;             // option "knn_cells": cell-list search (default) / brute force
   std::vector<int64_t> offs_cached;     // graph_offsets currently resident in `offs` (skips the upload when unchanged:
                                         // a frame stream repeats the same offsets, and the call stays graph-capturable)
   // tensor-core path (F=256, H=128, E<=8): pre-split, pre-swizzled operand images
@@ -1009,7 +1010,7 @@ void nmrgnn_destroy(nmrgnn_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (float* p : h->owned) cudaFree(p);
   for (DevBuf* b : {&h->atoms, &h->nlist, &h->edges, &h->invdeg, &h->efeat, &h->hA, &h->hB, &h->peaks, &h->tmp_in,
-                    &h->tmp_out, &h->pos, &h->offs, &h->rec, &h->hmaxA, &h->hmaxB, &h->genA, &h->genB})
+                    &h->tmp_out, &h->pos, &h->offs, &h->knn_sorted, &h->knn_cells, &h->knn_grid, &h->rec, &h->hmaxA, &h->hmaxB, &h->genA, &h->genB})
     if (b->p) cudaFree(b->p);
   for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
   if (h->ev_last) cudaEventDestroy(h->ev_last);
@@ -1727,6 +1728,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
     h->fc_rz = 1.0f + (float)value / 10.0f / 16777216.0f;
     return NMRGNN_OK;
   }
+  if (std::strcmp(name, "knn_cells") == 0) {
+    h->knn_cells_on = value != 0;
+    return NMRGNN_OK;
+  }
   if (std::strcmp(name, "mp_nsplit") == 0) {
     h->mp_nsplit = value != 0;
     return NMRGNN_OK;
@@ -1839,8 +1844,28 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
   a.inv_degree = (float*)d_inv;
   a.k = k;
   a.cutoff2 = cutoff_nm > 0.f ? cutoff_nm * cutoff_nm : 0.f;
-  knn_graph_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(a);
-  h->launches++;
+  if (h->knn_cells_on) {
+    if ((rc = ensure(h, h->knn_sorted, n_atoms * sizeof(float4)))) return rc;
+    if ((rc = ensure(h, h->knn_cells, n_graphs * (KNN_MAX_CELLS + 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(h, h->knn_grid, n_graphs * sizeof(KnnGrid)))) return rc;
+    KnnCellArgs b{};
+    b.pos = a.pos;
+    b.offsets = a.offsets;
+    b.sorted = (float4*)h->knn_sorted.p;
+    b.cell_start = (uint32_t*)h->knn_cells.p;
+    b.grid = (KnnGrid*)h->knn_grid.p;
+    knn_build_cells_kernel<<<(unsigned)n_graphs, KNN_BUILD_THREADS, 0, s>>>(b);
+    KnnQueryArgs qa{};
+    qa.out = a;
+    qa.sorted = b.sorted;
+    qa.cell_start = b.cell_start;
+    qa.grid = b.grid;
+    knn_query_cells_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(qa);
+    h->launches += 2;
+  } else {
+    knn_graph_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(a);
+    h->launches++;
+  }
   if ((rc = io.finish(nlist, d_nl, n_atoms * k * sizeof(int32_t)))) return rc;
   if ((rc = io.finish(edges, d_ed, n_atoms * k * sizeof(float)))) return rc;
   if ((rc = io.finish(inv_degree, d_inv, n_atoms * sizeof(float)))) return rc;

@@ -36,8 +36,11 @@ __device__ __forceinline__ bool knn_before(float da, int ia, float db, int ib) {
 // blocks); splitting the candidates 8 ways fills the GPU and an 8-way merge in shared memory restores the exact order.
 __global__ void __launch_bounds__(KNN_THREADS) knn_graph_kernel(const KnnArgs p) {
   __shared__ float4 tile[KNN_TILE];
-  __shared__ float md[KNN_QPB][KNN_PARTS][KNN_KMAX];
-  __shared__ int mi[KNN_QPB][KNN_PARTS][KNN_KMAX];
+  // running top-k of every thread, slot-major (conflict-free when the lanes touch the same slot).  In shared memory, not
+  // in a per-thread array: a dynamically indexed array lives in local memory, and 256 B x 768 threads per SM thrash the
+  // L1 (ncu: 78 % of the local sectors missed, the kernel ran 10x longer than its arithmetic).
+  __shared__ float md[KNN_KMAX][KNN_THREADS];
+  __shared__ int mi[KNN_KMAX][KNN_THREADS];
   __shared__ int mc[KNN_QPB][KNN_PARTS];
   const int g = blockIdx.x;
   const int64_t a0 = p.offsets[g], a1 = p.offsets[g + 1];
@@ -53,8 +56,7 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_graph_kernel(const KnnArgs p)
     qy = q[1];
     qz = q[2];
   }
-  float bd[KNN_KMAX];
-  int bi[KNN_KMAX];
+  const int tx = threadIdx.x;
   const int k = p.k;
   int count = 0;
   float worst = 3.4e38f;
@@ -86,25 +88,21 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_graph_kernel(const KnnArgs p)
       if (p.cutoff2 > 0.f && d2 > p.cutoff2) continue;
       if (count == k && !knn_before(d2, j, worst, worst_i)) continue;
       int pos = count < k ? count : k - 1;
-      while (pos > 0 && knn_before(d2, j, bd[pos - 1], bi[pos - 1])) {
-        bd[pos] = bd[pos - 1];
-        bi[pos] = bi[pos - 1];
+      while (pos > 0 && knn_before(d2, j, md[pos - 1][tx], mi[pos - 1][tx])) {
+        md[pos][tx] = md[pos - 1][tx];
+        mi[pos][tx] = mi[pos - 1][tx];
         --pos;
       }
-      bd[pos] = d2;
-      bi[pos] = j;
+      md[pos][tx] = d2;
+      mi[pos][tx] = j;
       if (count < k) ++count;
       if (count == k) {
-        worst = bd[k - 1];
-        worst_i = bi[k - 1];
+        worst = md[k - 1][tx];
+        worst_i = mi[k - 1][tx];
       }
     }
   }
   // 8-way merge of the partial lists (each sorted by (d2, index)) by the query's first thread
-  for (int s = 0; s < count; ++s) {
-    md[ql][part][s] = bd[s];
-    mi[ql][part][s] = bi[s];
-  }
   mc[ql][part] = count;
   __syncthreads();
   if (!active || part != 0) return;
@@ -120,8 +118,8 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_graph_kernel(const KnnArgs p)
 #pragma unroll
     for (int t = 0; t < KNN_PARTS; ++t) {
       if (head[t] < mc[ql][t]) {
-        const float dv = md[ql][t][head[t]];
-        const int iv = mi[ql][t][head[t]];
+        const float dv = md[head[t]][ql * KNN_PARTS + t];
+        const int iv = mi[head[t]][ql * KNN_PARTS + t];
         if (best < 0 || knn_before(dv, iv, bdv, biv)) {
           best = t;
           bdv = dv;
@@ -143,6 +141,313 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_graph_kernel(const KnnArgs p)
     p.edges[row + s] = d;
   }
   p.inv_degree[a0 + q_local] = deg > 0 ? __fdiv_rn(1.0f, (float)deg) : 0.0f;
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Cell-list form: the brute-force kernel above evaluates n distances per query atom; a protein frame
+// needs ~300.  Per graph, one block bins the atoms into a uniform grid (counting sort: histogram, scan, scatter into
+// `sorted` = {x, y, z, bits(local index)} in cell order); the query kernel scans the (2r+1)^3 block of cells around
+// the query's cell, starting with r = 1.  Everything outside that block is farther than r * cell from the query, so the
+// k best are final as soon as the k-th distance is strictly below r * cell (or the block covers the grid); otherwise
+// r grows and the block is rescanned.  Same distance expression, same (distance^2, index) order: the output is
+// bit-identical to the brute-force kernel (tests/test_gpu_parity.py::test_knn_cell_list_equals_brute_force).
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int KNN_MAX_CELLS = 8192;
+constexpr int KNN_BUILD_THREADS = 1024;
+constexpr float KNN_ATOMS_PER_CELL = 6.0f;   // of the bounding box; dense regions of a protein hold 2-3x that
+
+struct KnnGrid {
+  float ox, oy, oz, inv_c;
+  float c;
+  int nx, ny, nz;
+};
+
+struct KnnCellArgs {
+  const float* pos;          // [n_atoms, 3] nm
+  const int64_t* offsets;    // device [n_graphs + 1]
+  float4* sorted;            // [n_atoms] atoms of every graph in cell order
+  uint32_t* cell_start;      // [n_graphs][KNN_MAX_CELLS + 1]
+  KnnGrid* grid;             // [n_graphs]
+};
+
+__device__ __forceinline__ int knn_cell_coord(float x, float o, float inv_c, int n) {
+  const int c = (int)floorf(__fmul_rn(__fsub_rn(x, o), inv_c));
+  return min(max(c, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(KNN_BUILD_THREADS) knn_build_cells_kernel(const KnnCellArgs p) {
+  __shared__ uint32_t cnt[KNN_MAX_CELLS];
+  __shared__ float red[6][32];
+  __shared__ uint32_t wsum[32];
+  __shared__ KnnGrid gs;
+  const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t a0 = p.offsets[g];
+  const int n = (int)(p.offsets[g + 1] - a0);
+  if (n <= 0) return;
+  // ---- bounding box
+  float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+  for (int i = tid; i < n; i += KNN_BUILD_THREADS) {
+    const float* q = p.pos + (a0 + i) * 3;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], q[d]);
+      hi[d] = fmaxf(hi[d], q[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if (lane == 0) {
+      red[d][warp] = lo[d];
+      red[3 + d][warp] = hi[d];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float l[3], e[3];
+    for (int d = 0; d < 3; ++d) {
+      float a = red[d][0], b = red[3 + d][0];
+      for (int w = 1; w < KNN_BUILD_THREADS / 32; ++w) {
+        a = fminf(a, red[d][w]);
+        b = fmaxf(b, red[3 + d][w]);
+      }
+      l[d] = a;
+      e[d] = fmaxf(b - a, 1e-3f);
+    }
+    float c = cbrtf(KNN_ATOMS_PER_CELL * e[0] * e[1] * e[2] / (float)n);
+    c = fmaxf(c, 0.05f);
+    int nx, ny, nz;
+    for (;;) {
+      nx = (int)(e[0] / c) + 1;
+      ny = (int)(e[1] / c) + 1;
+      nz = (int)(e[2] / c) + 1;
+      if ((int64_t)nx * ny * nz <= KNN_MAX_CELLS) break;
+      c *= 1.26f;
+    }
+    gs.ox = l[0];
+    gs.oy = l[1];
+    gs.oz = l[2];
+    gs.c = c;
+    gs.inv_c = 1.0f / c;
+    gs.nx = nx;
+    gs.ny = ny;
+    gs.nz = nz;
+    p.grid[g] = gs;
+  }
+  __syncthreads();
+  const KnnGrid G = gs;
+  const int cells = G.nx * G.ny * G.nz;
+  for (int i = tid; i < cells; i += KNN_BUILD_THREADS) cnt[i] = 0u;
+  __syncthreads();
+  // ---- histogram
+  for (int i = tid; i < n; i += KNN_BUILD_THREADS) {
+    const float* q = p.pos + (a0 + i) * 3;
+    const int cx = knn_cell_coord(q[0], G.ox, G.inv_c, G.nx), cy = knn_cell_coord(q[1], G.oy, G.inv_c, G.ny),
+              cz = knn_cell_coord(q[2], G.oz, G.inv_c, G.nz);
+    atomicAdd(&cnt[(cz * G.ny + cy) * G.nx + cx], 1u);
+  }
+  __syncthreads();
+  // ---- exclusive scan over the cells: 8 consecutive cells per thread, block scan of the partial sums
+  constexpr int PER = KNN_MAX_CELLS / KNN_BUILD_THREADS;
+  uint32_t v[PER], sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int c = tid * PER + j;
+    v[j] = c < cells ? cnt[c] : 0u;
+    sum += v[j];
+  }
+  uint32_t inc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  uint32_t run = wsum[warp] + inc - sum;
+  uint32_t* cs = p.cell_start + (size_t)g * (KNN_MAX_CELLS + 1);
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int c = tid * PER + j;
+    if (c < cells) {
+      cnt[c] = run;          // becomes the scatter cursor
+      cs[c] = run;
+    }
+    run += v[j];
+  }
+  if (tid == 0) cs[cells] = (uint32_t)n;
+  __syncthreads();
+  // ---- scatter (order inside a cell is arbitrary; the query kernel orders candidates by (distance^2, index))
+  for (int i = tid; i < n; i += KNN_BUILD_THREADS) {
+    const float* q = p.pos + (a0 + i) * 3;
+    const float x = q[0], y = q[1], z = q[2];
+    const int cx = knn_cell_coord(x, G.ox, G.inv_c, G.nx), cy = knn_cell_coord(y, G.oy, G.inv_c, G.ny),
+              cz = knn_cell_coord(z, G.oz, G.inv_c, G.nz);
+    const uint32_t slot = atomicAdd(&cnt[(cz * G.ny + cy) * G.nx + cx], 1u);
+    p.sorted[a0 + slot] = make_float4(x, y, z, __int_as_float(i));
+  }
+}
+
+struct KnnQueryArgs {
+  KnnArgs out;               // pos / offsets / outputs / k / cutoff2 as for the brute-force kernel
+  const float4* sorted;
+  const uint32_t* cell_start;
+  const KnnGrid* grid;
+};
+
+__global__ void __launch_bounds__(KNN_THREADS) knn_query_cells_kernel(const KnnQueryArgs a) {
+  // running top-k of every thread, slot-major (conflict-free when the lanes touch the same slot).  In shared memory, not
+  // in a per-thread array: a dynamically indexed array lives in local memory, and 256 B x 768 threads per SM thrash the
+  // L1 (ncu: 78 % of the local sectors missed, the kernel ran 10x longer than its arithmetic).
+  __shared__ float md[KNN_KMAX][KNN_THREADS];
+  __shared__ int mi[KNN_KMAX][KNN_THREADS];
+  __shared__ int mc[KNN_QPB][KNN_PARTS];
+  const KnnArgs& p = a.out;
+  const int g = blockIdx.x;
+  const int64_t a0 = p.offsets[g];
+  const int n = (int)(p.offsets[g + 1] - a0);
+  if ((int64_t)blockIdx.y * KNN_QPB >= n) return;
+  const int ql = threadIdx.x / KNN_PARTS, part = threadIdx.x % KNN_PARTS, lane = threadIdx.x & 31;
+  const unsigned gmask = 0xffu << (lane & 24);                 // the 8 lanes of this query
+  const int q_local = blockIdx.y * KNN_QPB + ql;
+  if (q_local >= n) return;                                     // whole 8-lane groups leave together
+  const KnnGrid G = a.grid[g];
+  const uint32_t* cs = a.cell_start + (size_t)g * (KNN_MAX_CELLS + 1);
+  const float4* sp = a.sorted + a0;
+  const float* q = p.pos + (a0 + q_local) * 3;
+  const float qx = q[0], qy = q[1], qz = q[2];
+  const int cx = knn_cell_coord(qx, G.ox, G.inv_c, G.nx), cy = knn_cell_coord(qy, G.oy, G.inv_c, G.ny),
+            cz = knn_cell_coord(qz, G.oz, G.inv_c, G.nz);
+  const int k = p.k;
+  const int tx = threadIdx.x;
+  const int64_t row = (a0 + q_local) * k;
+  for (int r = 1;; ++r) {
+    int count = 0;
+    float worst = 3.4e38f;
+    int worst_i = 0x7fffffff;
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, G.nx - 1), y0 = max(cy - r, 0), y1 = min(cy + r, G.ny - 1),
+              z0 = max(cz - r, 0), z1 = min(cz + r, G.nz - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        // cells x0 .. x1 of a row are contiguous in the sorted order
+        const int rb = (z * G.ny + y) * G.nx;
+        const int s0 = (int)cs[rb + x0], s1 = (int)cs[rb + x1 + 1];
+        for (int i = s0 + part; i < s1; i += KNN_PARTS) {
+          const float4 c = sp[i];
+          const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          const int j = __float_as_int(c.w);
+          if (j == q_local) continue;
+          if (p.cutoff2 > 0.f && d2 > p.cutoff2) continue;
+          if (count == k && !knn_before(d2, j, worst, worst_i)) continue;
+          int pos = count < k ? count : k - 1;
+          while (pos > 0 && knn_before(d2, j, md[pos - 1][tx], mi[pos - 1][tx])) {
+            md[pos][tx] = md[pos - 1][tx];
+            mi[pos][tx] = mi[pos - 1][tx];
+            --pos;
+          }
+          md[pos][tx] = d2;
+          mi[pos][tx] = j;
+          if (count < k) ++count;
+          if (count == k) {
+            worst = md[k - 1][tx];
+            worst_i = mi[k - 1][tx];
+          }
+        }
+      }
+    // 8-way merge of the partial lists by the query's first thread
+    mc[ql][part] = count;
+    __syncwarp(gmask);
+    const bool whole = x0 == 0 && y0 == 0 && z0 == 0 && x1 == G.nx - 1 && y1 == G.ny - 1 && z1 == G.nz - 1;
+    int done = 1;
+    if (part == 0) {
+      int head[KNN_PARTS];
+#pragma unroll
+      for (int t = 0; t < KNN_PARTS; ++t) head[t] = 0;
+      // first pass: is the k-th merged distance safely inside the scanned block?
+      float dk = 3.4e38f;
+      int found = 0;
+      for (int s = 0; s < k; ++s) {
+        int best = -1;
+        float bdv = 0.f;
+        int biv = 0;
+#pragma unroll
+        for (int t = 0; t < KNN_PARTS; ++t)
+          if (head[t] < mc[ql][t]) {
+            const float dv = md[head[t]][ql * KNN_PARTS + t];
+            const int iv = mi[head[t]][ql * KNN_PARTS + t];
+            if (best < 0 || knn_before(dv, iv, bdv, biv)) {
+              best = t;
+              bdv = dv;
+              biv = iv;
+            }
+          }
+        if (best < 0) break;
+#pragma unroll
+        for (int t = 0; t < KNN_PARTS; ++t)
+          if (t == best) ++head[t];
+        dk = bdv;
+        ++found;
+      }
+      // (0.9999: the cell of a point is floor((x - o) / c) in float32, so a cell boundary is only exact to a few ulp)
+      const float reach = __fmul_rn(__fmul_rn((float)r, G.c), 0.9999f);
+      const float lim2 = __fmul_rn(reach, reach);
+      // with a cutoff nothing beyond it matters: the block is sufficient once it reaches the cutoff
+      const bool cut_ok = p.cutoff2 > 0.f && lim2 > p.cutoff2;
+      done = whole || cut_ok || (found == k && dk < lim2);
+      if (done) {
+#pragma unroll
+        for (int t = 0; t < KNN_PARTS; ++t) head[t] = 0;
+        int deg = 0;
+        for (int s = 0; s < k; ++s) {
+          int best = -1;
+          float bdv = 0.f;
+          int biv = 0;
+#pragma unroll
+          for (int t = 0; t < KNN_PARTS; ++t)
+            if (head[t] < mc[ql][t]) {
+              const float dv = md[head[t]][ql * KNN_PARTS + t];
+              const int iv = mi[head[t]][ql * KNN_PARTS + t];
+              if (best < 0 || knn_before(dv, iv, bdv, biv)) {
+                best = t;
+                bdv = dv;
+                biv = iv;
+              }
+            }
+          int j = 0;
+          float d = 0.f;
+          if (best >= 0) {
+#pragma unroll
+            for (int t = 0; t < KNN_PARTS; ++t)
+              if (t == best) ++head[t];
+            j = biv;
+            d = sqrtf(bdv);
+          }
+          deg += (j > 0);  // library.py:115-116 counts nlist > 0 (a real neighbour with index 0 is not counted)
+          p.nlist[row + s] = (int32_t)(a0 + j);
+          p.edges[row + s] = d;
+        }
+        p.inv_degree[a0 + q_local] = deg > 0 ? __fdiv_rn(1.0f, (float)deg) : 0.0f;
+      }
+    }
+    done = __shfl_sync(gmask, done, lane & 24);
+    if (done) return;
+    __syncwarp(gmask);     // the merge buffers are reused by the next, larger block
+  }
 }
 
 }  // namespace nmr

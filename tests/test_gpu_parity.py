@@ -324,6 +324,39 @@ def test_knn_graph_matches_host_builder(model):
     np.testing.assert_allclose(e2[300:], e_b, rtol=2e-5, atol=1e-6)
 
 
+def test_knn_cell_list_equals_brute_force(model):
+    """The cell-list neighbour search (default) returns exactly what the brute-force search returns -- same distance
+    expression, same (distance^2, index) order: proteins, a batch of frames, sparse / degenerate geometries (fewer atoms
+    than k, one atom, a line, coincident points), a distance cutoff, k = 8 and k = 32."""
+    import os
+    from nmrgnn_b200 import _capi
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "g108m_structure.npz")) as z:
+        pos = np.ascontiguousarray(z["positions_A"].astype(np.float32) / np.float32(10))
+    with np.load(os.path.join(GOLDEN, "g7lgi_structure.npz")) as z:
+        frames = np.ascontiguousarray(z["positions_mA"].astype(np.float32) / np.float32(10000))
+    rng = np.random.default_rng(2)
+    sparse = rng.uniform(0, 30, (700, 3)).astype(np.float32)                 # far apart: blocks must grow
+    line = np.stack([np.linspace(0, 5, 400), np.zeros(400), np.zeros(400)], 1).astype(np.float32)
+    dup = np.repeat(rng.uniform(0, 1, (50, 3)).astype(np.float32), 4, axis=0)   # coincident points: ties by index
+    cases = [([pos], 16, 0.0), ([f for f in frames[:5]], 16, 0.0), ([pos[:9], pos[:1], pos[:40]], 16, 0.0),
+             ([sparse], 16, 0.0), ([line], 8, 0.0), ([dup], 8, 0.0), ([pos], 16, 0.25), ([sparse], 16, 2.0), ([pos[:900]], 32, 0.0)]
+    h = model.handle
+    for graphs, k, cutoff in cases:
+        allpos = np.ascontiguousarray(np.concatenate(graphs, 0))
+        offs = np.concatenate([[0], np.cumsum([len(g) for g in graphs])]).astype(np.int64)
+        n = allpos.shape[0]
+        res = {}
+        for mode in (1, 0):
+            h.set_option("knn_cells", mode)
+            nl, ed, inv = np.empty((n, k), np.int32), np.empty((n, k), np.float32), np.empty(n, np.float32)
+            h.knn_graph(allpos, offs, n, len(graphs), k, cutoff, nl, ed, inv, _capi.MEM_HOST)
+            res[mode] = (nl, ed, inv)
+        h.set_option("knn_cells", 1)
+        for a, b in zip(res[1], res[0]):
+            assert np.array_equal(a, b), (len(graphs), k, cutoff)
+
+
 def test_tcgen05_selftest_gemm(model):
     """Building blocks of the tensor-core path: one 128x128x64 GEMM through swizzled smem
     operands and a TMEM accumulator; 3xTF32 must be fp32-accurate, 1xTF32 must not be."""

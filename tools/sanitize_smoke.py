@@ -11,7 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import nmrgnn_b200  # noqa: E402
-from conftest import graph_of, load_golden, tol_ratio  # noqa: E402
+from conftest import load_golden, tol_ratio  # noqa: E402
+
+
+def graph_of(g):
+    return g["atoms"], g["nlist"], g["edges"], g["inv_degree"]
 
 
 def main():
