@@ -331,7 +331,7 @@ class GNNModel:
 
 
 def build_GNNModel(hp: Optional[Dict[str, object]] = None, metrics: bool = False, loss_balance: float = 1.0,
-                   num_elem: int = 16, seed: int = 0, device: int = 0) -> GNNModel:
+                   num_elem: int = 16, seed: int = 0, device: int = 0, peak_std=None, peak_avg=None) -> GNNModel:
     """Fresh randomly initialised model with the reference's hyper-parameter names
     and defaults (nmrgnn/model.py:12-41).  Optimizer / loss / metric wiring
     (model.py:43-104) is training-only and out of scope."""
@@ -345,5 +345,6 @@ def build_GNNModel(hp: Optional[Dict[str, object]] = None, metrics: bool = False
         edge_fc_layers=int(hp.get("edge_fc_layers", 4)),
         mp_activation=str(hp.get("mp_activation", "softplus")),
         fc_activation=str(hp.get("fc_activation", "softplus")),
-        rbf_low=float(hp.get("rbf_low", 0.005)), rbf_high=float(hp.get("rbf_high", 0.20)), seed=seed)
+        rbf_low=float(hp.get("rbf_low", 0.005)), rbf_high=float(hp.get("rbf_high", 0.20)), seed=seed,
+        peak_std=peak_std, peak_avg=peak_avg)
     return GNNModel(p, device=device)

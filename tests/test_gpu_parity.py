@@ -644,6 +644,37 @@ def test_generic_geometry_models(hp):
         m.close()
 
 
+def test_second_weight_set_on_tensor_cores_against_oracle():
+    """The truncation compensation is not fitted to the pretrained weights: freshly initialised models at the pretrained
+    geometry (F = 256, H = 128, E = 3 -- the tcgen05 kernels, forced on by tc_min_atoms = 0) with softplus / tanh / relu
+    activations and baseline-like standards against the fp64 oracle on a 2 300-atom protein graph, K = 16 and K = 8."""
+    import nmrgnn_b200
+    from nmrgnn_b200 import workloads
+    from nmrgnn_b200.params import baseline_standards
+    from oracle import forward as orc
+    std, avg = baseline_standards(10)
+    for seed, mp_act, fc_act in ((11, "softplus", "softplus"), (12, "tanh", "softplus"), (13, "relu", "relu")):
+        m = nmrgnn_b200.build_GNNModel(dict(atom_feature_size=256, edge_feature_size=3, edge_hidden_size=128, mp_layers=4,
+                                            fc_layers=4, edge_fc_layers=4, mp_activation=mp_act, fc_activation=fc_act),
+                                       num_elem=10, seed=seed, peak_std=std, peak_avg=avg)
+        try:
+            m.handle.set_option("tc_min_atoms", 0)
+            assert "tcgen05-fp16x3" in m.handle.compute_path and "mp" in m.handle.compute_path
+            for k in (16, 8):
+                atoms, nlist, edges, inv = workloads.protein_graph(21 + k, neighbor_number=k)
+                ref = orc.forward(m.params, atoms, nlist, edges, inv, dtype=np.float64)
+                y = m((atoms, nlist, edges, inv))
+                r = tol_ratio(y, ref)
+                m.handle.set_option("force_ffma", 1)
+                r_ffma = tol_ratio(m((atoms, nlist, edges, inv)), ref)
+                m.handle.set_option("force_ffma", 0)
+                print(f"seed {seed} {mp_act}/{fc_act} K={k}: tensor cores {r:.3f}, exact-FP32 kernels {r_ffma:.3f} "
+                      f"(path {m.handle.compute_path}, compensation {m.handle.tc_compensation()})")
+                assert r <= 1.0 and r_ffma <= 1.0
+        finally:
+            m.close()
+
+
 def test_bad_index_detected_on_both_routes(any_model):
     """An out-of-range neighbour index raises IndexError (TF's CPU GatherV2 raises too) on the tensor-core route
     (index check inside the edge kernel, chunked or not) and on the exact-FP32 route; the handle stays usable."""
