@@ -189,6 +189,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // 32 lanes x 16 consecutive fp32 columns: thread i of warp q gets TMEM lane 32q+i
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
+  __syncwarp();            // .sync.aligned needs a converged warp (see tmem_ld16_nowait)
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -201,6 +202,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
+  __syncwarp();
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
@@ -399,8 +401,12 @@ __device__ __forceinline__ void split8_f16(const float (&x)[8], uint4& hi, uint4
   split2_f16(x[6], x[7], hi.w, lo.w);
 }
 
-// 32 lanes x 16 columns without the wait (issue several, then tmem_ld_wait once)
+// 32 lanes x 16 columns without the wait (issue several, then tmem_ld_wait once).
+// tcgen05.ld / st / wait are .sync.aligned: every lane of the warp must execute them TOGETHER.  A warp that has just left
+// an mbarrier spin loop (or any data-dependent branch) is not guaranteed to have reconverged -- observed on B200 in a
+// round-2 experiment: lanes 16..31 of a warp read garbage from tensor memory -- hence the explicit __syncwarp().
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  __syncwarp();
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
