@@ -422,8 +422,8 @@ def run_md_stream(args, model, world, rank, local_rank, dev):
             "data": "synthetic (108M.pdb coordinates + seeded jitter)",
             "config": workload_config(world, 5, n_frames, atoms_per_frame=n, frames_per_batch=fs.B, cuda_graph=fs.graph_captured,
                                       compute_path=model.handle.compute_path,
-                                      l2_note="one batch (8 frames) is 46 MB of node / record buffers: L2-resident; frames "
-                                              "differ from batch to batch"),
+                                      l2_note=f"one batch ({fs.B} frames) is {fs.B * n * 2308 / 1e6:.0f} MB of node / record "
+                                              "buffers: L2-resident; frames differ from batch to batch"),
             "clocks": clocks,
             "device": {"frames_per_s": n_frames / devt, "ms_per_frame": devt * 1e3 / n_frames,
                        "note": "compute stream only (graph build + forward), max over ranks", **split},

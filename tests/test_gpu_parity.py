@@ -541,7 +541,8 @@ def test_eval_struct_stream(model, tmp_path):
     u = nmrgnn_b200.Universe(frames, elements, ["X%d" % i for i in range(n)], ["RES"] * n, np.arange(n) // 10)
     out_csv = str(tmp_path / "peaks.csv")
     res = nmrgnn_b200.eval_struct(u, output_csv=out_csv, model=model, raise_on_bad_peaks=False)
-    assert res["frames_per_batch"] == 8 and res["cuda_graph"]
+    from nmrgnn_b200.mdstream import default_frames_per_batch
+    assert res["frames_per_batch"] == default_frames_per_batch(n) == 15 and res["cuda_graph"]      # 291 tiles: 2 full waves
     assert res["frames"] == 3 and len(res["peaks"]) == 3 * n
     with open(out_csv) as f:
         rows = list(csv.reader(f))
