@@ -920,24 +920,12 @@ constexpr int MTC_KMAX = 16;
 // feature pass (~38 KB unique per tile) then mostly hit L1.
 constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * MTC_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 static_assert(MTC_SMEM + 1024 <= 196 * 1024, "MP tensor-core kernel no longer fits the 196 KB shared-memory configuration");
-// CTA-pair form (cta_group::2): two CTAs of a cluster work on two neighbouring 128-atom tiles with ONE M = 256
-// instruction stream issued by the leader (rank 0).  Each CTA stages only its half of W' (N rows 128 r .. 128 r + 127 of
-// the hi and lo images: 16 KB per (pass, n) chunk instead of 32 KB), so the tensor core reads half as many B-operand
-// bytes from each SM's shared memory and the bulk copies write half as many — the MP layer is bound by that data
-// pipe.  Hand-offs that cross the pair: the producers and the epilogue warps of both CTAs arrive on the
-// LEADER's a_full / d_empty barriers (cluster-scope release), the peer's idle MMA warp relays "my half of W' has
-// landed" to the leader's b_peer barriers, and the leader's commits are multicast to both CTAs.
-constexpr int MTC_PAIR_BRING = 3;
-constexpr int MTC_PAIR_BSLOT = 16384;
-constexpr int MTC_PAIR_ASTAGES = 3;    // the halved W' ring pays for a third operand stage: the two CTAs of a pair decouple
-constexpr size_t MTC_PAIR_SMEM = 512 + MTC_PAIR_ASTAGES * 3 * 16384 + MTC_PAIR_BRING * MTC_PAIR_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
-
-template <int ACT, bool PAIR, bool SEG>
+template <int ACT, bool SEG>
 __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
-  constexpr int BRING = PAIR ? MTC_PAIR_BRING : MTC_BRING;
-  constexpr int BSLOT = PAIR ? MTC_PAIR_BSLOT : MTC_BSLOT;
-  constexpr bool SPLIT = !PAIR;     // one slot = one image (hi or lo) of a chunk; pair: this CTA's halves of both
-  constexpr uint32_t AST = PAIR ? MTC_PAIR_ASTAGES : 2;      // operand stages
+  constexpr int BRING = MTC_BRING;
+  constexpr int BSLOT = MTC_BSLOT;
+  constexpr bool SPLIT = true;      // one slot = one image (hi or lo) of a (pass, n) chunk
+  constexpr uint32_t AST = 2;      // operand stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 511) & ~uintptr_t(511));
   uint8_t* a_st = smem;                                   // [2 stages][3 chunks][hi 8192 | lo 8192]
@@ -950,8 +938,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   uint64_t* a_empty = a_full + AST;   // [AST]
   uint64_t* b_full = a_empty + AST;   // [BRING]
   uint64_t* b_empty = b_full + BRING;
-  uint64_t* b_peer = b_empty + BRING; // [BRING]  (pair, leader: the peer's half of the slot has landed)
-  uint64_t* rec_full = b_peer + BRING;
+  uint64_t* rec_full = b_empty + BRING;
   uint64_t* rec_empty = rec_full + 1;
   uint64_t* d_full = rec_empty + 1;
   uint64_t* d_empty = d_full + 1;
@@ -959,43 +946,35 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
   if (tid == 0) {
     for (int i = 0; i < (int)AST; ++i) {
-      tc::mbar_init(&a_full[i], PAIR ? 16 : 8);      // pair: the producer warps of both CTAs
+      tc::mbar_init(&a_full[i], 8);
       tc::mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) tc::mbar_init(&sc_full[i], 8);
     for (int i = 0; i < BRING; ++i) {
       tc::mbar_init(&b_full[i], 1);
       tc::mbar_init(&b_empty[i], 1);
-      tc::mbar_init(&b_peer[i], 1);
     }
     tc::mbar_init(rec_full, 1);
     tc::mbar_init(rec_empty, 8);
     tc::mbar_init(d_full, 1);
-    tc::mbar_init(d_empty, PAIR ? 8 : 4);            // pair: the epilogue warps of both CTAs
+    tc::mbar_init(d_empty, 4);
     tc::mbar_fence_init();
   }
   if (warp == 1) {
-    if (PAIR) tc::tmem_alloc_pair<512>(tmem_slot);
-    else tc::tmem_alloc<512>(tmem_slot);
+    tc::tmem_alloc<512>(tmem_slot);
   }
   tc::tc_fence_before();
-  if (PAIR) tc::cluster_sync();     // both CTAs' barriers exist before any remote arrive / multicast commit
-  else __syncthreads();
+  __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int K = p.K, E = p.E;
   const int64_t n_tiles = (p.n_atoms + 127) / 128;
-  // tile walk: a single CTA takes tiles blockIdx.x, + gridDim.x, ...; a pair takes tile pairs and CTA r the r-th
-  // tile of each pair (a trailing odd tile leaves the peer with an empty tile: it still runs the whole protocol)
-  const int64_t tile_first = PAIR ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
-  const int64_t tile_step = PAIR ? (int64_t)gridDim.x : (int64_t)gridDim.x;
-  const int64_t tile_end = PAIR ? ((n_tiles + 1) / 2) * 2 : n_tiles;
-  // the leader's barriers as seen from either CTA of the pair
-  const uint32_t a_full_ldr = PAIR ? tc::map_to_cta(tc::smem_u32(a_full), 0) : 0u;
-  const uint32_t d_empty_ldr = PAIR ? tc::map_to_cta(tc::smem_u32(d_empty), 0) : 0u;
+  // tile walk: the CTA takes tiles blockIdx.x, + gridDim.x, ...
+  const int64_t tile_first = (int64_t)blockIdx.x;
+  const int64_t tile_step = (int64_t)gridDim.x;
+  const int64_t tile_end = n_tiles;
 
   if (warp == 0) {
     // ===================== W' loader =====================
@@ -1008,9 +987,6 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           tc::mbar_expect_tx(&b_full[slot], BSLOT);
           if (SPLIT) {  // [pass][n][hi | lo] is contiguous in 16 KB images
             tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * BSLOT, BSLOT, &b_full[slot]);
-          } else if (PAIR) {   // this CTA's 128 N rows of the hi and of the lo image
-            tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * 32768 + rank * 8192, 8192, &b_full[slot]);
-            tc::bulk_g2s(b_ring + slot * BSLOT + 8192, p.Wimg + (size_t)q * 32768 + 16384 + rank * 8192, 8192, &b_full[slot]);
           } else {
             tc::bulk_g2s(b_ring + slot * BSLOT, p.Wimg + (size_t)q * 32768, 32768, &b_full[slot]);
           }
@@ -1043,22 +1019,10 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         for (int i = lane; i * 128 < nrows * K * 16; i += 32) tc::prefetch_l2(rb + (size_t)i * 128);
       }
     }
-  } else if (warp == 1 && PAIR && rank != 0) {
-    // ===================== peer CTA: relay "my half of the W' slot has landed" to the leader =====================
-    if (lane == 0) {
-      const uint32_t b_peer_ldr = tc::map_to_cta(tc::smem_u32(b_peer), 0);
-      uint32_t it = 0;
-      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
-        for (int q = 0; q < MTC_PASSES * E; ++q, ++it) {
-          const uint32_t slot = it % BRING;
-          tc::mbar_wait(&b_full[slot], (it / BRING) & 1);
-          tc::mbar_arrive_cluster(b_peer_ldr + slot * 8u);
-        }
-    }
   } else if (warp == 1) {
-    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(PAIR ? 256 : 128, 256);
+      const uint32_t idesc = tc::make_idesc_f16(128, 256);
       const uint32_t d_main = tmem_base, d_corr = tmem_base + 256u;
       uint32_t it = 0, pass = 0, t = 0, dph = 0;
       const int seg_passes = MTC_PASSES / p.nseg;
@@ -1068,22 +1032,19 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
           if (ps % seg_passes == 0) {            // a new accumulation chain: the epilogue has drained the previous one
             if (p.dbg) c0 = clock64();
-            if (PAIR) tc::mbar_wait_cluster(d_empty, (dph & 1) ^ 1);
-            else tc::mbar_wait(d_empty, (dph & 1) ^ 1);
+            tc::mbar_wait(d_empty, (dph & 1) ^ 1);
             if (p.dbg) w_d += clock64() - c0;
             tc::tc_fence_after();
           }
           const uint32_t st = pass % AST;
           if (p.dbg) c0 = clock64();
-          if (PAIR) tc::mbar_wait_cluster(&a_full[st], (pass / AST) & 1);
-          else tc::mbar_wait(&a_full[st], (pass / AST) & 1);
+          tc::mbar_wait(&a_full[st], (pass / AST) & 1);
           if (p.dbg) w_a += clock64() - c0;
           tc::tc_fence_after();
           for (int n = 0; n < E; ++n, ++it) {
             uint32_t slot = it % BRING;
             if (p.dbg) c0 = clock64();
             tc::mbar_wait(&b_full[slot], (it / BRING) & 1);
-            if (PAIR) tc::mbar_wait_cluster(&b_peer[slot], (it / BRING) & 1);
             if (p.dbg) w_b += clock64() - c0;
             tc::tc_fence_after();
             const uint8_t* ac = a_st + (st * 3 + n) * 16384;
@@ -1097,13 +1058,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
               // main restarts with every chain; the correction accumulator (its truncation is scaled by 2^-11)
               // runs through the whole tile and is read once, by the last chain's epilogue
               const uint32_t acc = ((ps % seg_passes) | n | ks) != 0, acc_c = (ps | n | ks) != 0;
-              if (PAIR) {
-                tc::umma_f16_pair(d_main, ah + adv, bh + adv, idesc, acc);
-                tc::umma_f16_pair(d_corr, al + adv, bh + adv, idesc, acc_c);
-              } else {
-                tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
-                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc_c);
-              }
+              tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
+              tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc_c);
             }
             uint64_t bl;
             if (SPLIT) {     // the lo image is the next slot of the ring
@@ -1122,17 +1078,13 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
-              if (PAIR) tc::umma_f16_pair(d_corr, ah + adv, bl + adv, idesc, 1);
-              else tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+              tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
             }
-            if (PAIR) tc::umma_commit_pair(&b_empty[slot], 3);
-            else tc::umma_commit(&b_empty[slot]);
+            tc::umma_commit(&b_empty[slot]);
           }
-          if (PAIR) tc::umma_commit_pair(&a_empty[st], 3);
-          else tc::umma_commit(&a_empty[st]);
+          tc::umma_commit(&a_empty[st]);
           if ((ps + 1) % seg_passes == 0) {      // chain complete: hand the accumulators to the epilogue
-            if (PAIR) tc::umma_commit_pair(d_full, 3);
-            else tc::umma_commit(d_full);
+            tc::umma_commit(d_full);
             ++dph;
           }
         }
@@ -1160,7 +1112,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     uint32_t t = 0, dph = 0;
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
-      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));   // 0: the pair's trailing empty tile
+      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
       tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
       float hm[8];
 #pragma unroll
@@ -1230,8 +1182,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) tc::mbar_arrive_cluster(d_empty_ldr);
-          else tc::mbar_arrive(d_empty);
+          tc::mbar_arrive(d_empty);
         }
         if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
       } else {
@@ -1340,8 +1291,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) tc::mbar_arrive_cluster(d_empty_ldr);
-            else tc::mbar_arrive(d_empty);
+            tc::mbar_arrive(d_empty);
           }
           if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
         }
@@ -1509,8 +1459,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) tc::mbar_arrive_cluster(a_full_ldr + st * 8u);
-          else tc::mbar_arrive(&a_full[st]);
+          tc::mbar_arrive(&a_full[st]);
         }
       }
       __syncwarp();
@@ -1518,22 +1467,20 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     }
   }
   tc::tc_fence_before();
-  if (PAIR) tc::cluster_sync();     // the leader's MMAs read the peer's shared memory until the very end
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
-    if (PAIR) tc::tmem_dealloc_pair<512>(tmem_base);
-    else tc::tmem_dealloc<512>(tmem_base);
+    tc::tmem_dealloc<512>(tmem_base);
   }
 }
 
 template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
-  mp_layer_tc_body<ACT, false, false>(p);
+  mp_layer_tc_body<ACT, false>(p);
 }
 // the same with the K loop cut into p.nseg accumulation chains (option "mp_chain_segments" > 1)
 template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_seg_kernel(const MpTcArgs p) {
-  mp_layer_tc_body<ACT, false, true>(p);
+  mp_layer_tc_body<ACT, true>(p);
 }
 
 }  // namespace nmr
@@ -1583,18 +1530,9 @@ constexpr size_t FTC_SMEM = 1024 + FTC_X_BYTES + FTC_RING * 16384 + MAX_DENSE * 
 static_assert(FTC_SMEM <= 227 * 1024, "node-MLP tensor-core kernel exceeds the 227 KB shared-memory limit");
 static_assert(128 * FTC_LDZ * 4 <= FTC_X_BYTES, "Z overlays the X operand");
 
-// CTA-pair form (cta_group::2, option "fc_pair"): two CTAs work on two neighbouring tiles with one M = 256 instruction
-// stream issued by the leader.  The B operand of a pair is split by N rows between the CTAs, and the merged
-// operand [w_hi | w_lo] splits exactly into w_hi (leader) and w_lo (peer): a slot is 12 KB per CTA —
-//   [0, 8 KB): the CTA's 128 rows of [w_hi | w_lo]    [8 KB, 12 KB): its 64 rows of w_hi for the x_lo * w_hi product
-// — and each MMA phase (the part the epilogue cannot overlap) serves two tiles.  Hand-offs across the pair as in
-// the MP pair kernel: worker warps of both CTAs arrive on the leader's x_full, the peer's idle MMA warp relays its
-// w_full, the leader's commits are multicast.
-constexpr int FTC_PAIR_SLOT = 12288;
-
-template <int ACT, bool PAIR>
+template <int ACT>
 __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
-  constexpr int SLOT = PAIR ? FTC_PAIR_SLOT : 16384;
+  constexpr int SLOT = 16384;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xs = smem;                                      // [8 chunks][hi 8192 | lo 8192]; later Z [128][FTC_LDZ] fp32
@@ -1604,41 +1542,33 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(rs + MAX_DENSE * 128);
   uint64_t* w_full = bars;                                 // [RING]
   uint64_t* w_empty = w_full + FTC_RING;                   // [RING]
-  uint64_t* w_peer = w_empty + FTC_RING;                   // [RING]  (pair, leader: the peer's slot has landed)
-  uint64_t* x_full = w_peer + FTC_RING;
+  uint64_t* x_full = w_empty + FTC_RING;
   uint64_t* d_full = x_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
   if (tid == 0) {
     for (int i = 0; i < FTC_RING; ++i) {
       tc::mbar_init(&w_full[i], 1);
       tc::mbar_init(&w_empty[i], 1);
-      tc::mbar_init(&w_peer[i], 1);
     }
-    tc::mbar_init(x_full, PAIR ? 32 : 16);               // pair: the worker warps of both CTAs
+    tc::mbar_init(x_full, 16);
     tc::mbar_init(d_full, 1);
     tc::mbar_fence_init();
   }
   const int nl = p.n_layers;
   for (int i = tid; i < nl * 256; i += FTC_THREADS) bias_s[i] = p.bias[i];
   if (warp == 1) {
-    if (PAIR) tc::tmem_alloc_pair<512>(tmem_slot);
-    else tc::tmem_alloc<512>(tmem_slot);
+    tc::tmem_alloc<512>(tmem_slot);
   }
   tc::tc_fence_before();
-  if (PAIR) tc::cluster_sync();
-  else __syncthreads();
+  __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int64_t n_tiles = (p.n_atoms + 127) / 128;
-  // tile walk (see mp_layer_tc_body): a pair takes tile pairs, CTA r the r-th tile; a trailing odd tile leaves the
-  // peer with an empty tile and the whole protocol still runs
-  const int64_t tile_first = PAIR ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
+  const int64_t tile_first = (int64_t)blockIdx.x;
   const int64_t tile_step = (int64_t)gridDim.x;
-  const int64_t tile_end = PAIR ? ((n_tiles + 1) / 2) * 2 : n_tiles;
-  const uint32_t x_full_ldr = PAIR ? tc::map_to_cta(tc::smem_u32(x_full), 0) : 0u;
+  const int64_t tile_end = n_tiles;
 
   if (warp == 0) {
     // ===================== W loader =====================
@@ -1652,43 +1582,21 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
             const uint32_t slot = it % FTC_RING, ph = (it / FTC_RING) & 1;
             tc::mbar_wait(&w_empty[slot], ph ^ 1);
             tc::mbar_expect_tx(&w_full[slot], SLOT);
-            if (PAIR) {
-              // leader: w_hi and its rows 0..63 again; peer: w_lo and rows 64..127 of w_hi
-              tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * 16384 + rank * 8192, 8192, &w_full[slot]);
-              tc::bulk_g2s(ring + slot * SLOT + 8192, src + (size_t)q * 16384 + rank * 4096, 4096, &w_full[slot]);
-            } else {
-              tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * 16384, 16384, &w_full[slot]);
-            }
-          }
-        }
-    }
-  } else if (warp == 1 && PAIR && rank != 0) {
-    // ===================== peer CTA: relay "my slot has landed" to the leader =====================
-    if (lane == 0) {
-      const uint32_t w_peer_ldr = tc::map_to_cta(tc::smem_u32(w_peer), 0);
-      uint32_t it = 0;
-      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
-        for (int l = 0; l < nl; ++l) {
-          const int n_slots = (l == nl - 1) ? 8 : 16;
-          for (int q = 0; q < n_slots; ++q, ++it) {
-            const uint32_t slot = it % FTC_RING;
-            tc::mbar_wait(&w_full[slot], (it / FTC_RING) & 1);
-            tc::mbar_arrive_cluster(w_peer_ldr + slot * 8u);
+            tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * 16384, 16384, &w_full[slot]);
           }
         }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       // per 128-column half h: tensor-memory columns [256h, 256h+128) = main, [256h+128, 256h+256) = corr, so that
       // x_hi * [w_hi | w_lo] -> [main | corr] is ONE N = 256 instruction (the slot holds the hi and lo tiles adjacently)
-      const uint32_t idesc = tc::make_idesc_f16(PAIR ? 256 : 128, 128), idesc2 = tc::make_idesc_f16(PAIR ? 256 : 128, 256);
+      const uint32_t idesc = tc::make_idesc_f16(128, 128), idesc2 = tc::make_idesc_f16(128, 256);
       uint32_t it = 0, px = 0;
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
         for (int l = 0; l < nl; ++l) {
           const int halves = (l == nl - 1) ? 1 : 2;
-          if (PAIR) tc::mbar_wait_cluster(x_full, px);
-          else tc::mbar_wait(x_full, px);
+          tc::mbar_wait(x_full, px);
           px ^= 1;
           tc::tc_fence_after();
           for (int c = 0; c < 8; ++c) {
@@ -1697,32 +1605,19 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
             for (int hf = 0; hf < halves; ++hf, ++it) {
               const uint32_t slot = it % FTC_RING;
               tc::mbar_wait(&w_full[slot], (it / FTC_RING) & 1);
-              if (PAIR) tc::mbar_wait_cluster(&w_peer[slot], (it / FTC_RING) & 1);
               tc::tc_fence_after();
               const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT));
               const uint32_t d_main = tmem_base + (uint32_t)hf * 256u, d_corr = d_main + 128u;
-              if (PAIR) {
-                const uint64_t bx = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT + 8192));   // this CTA's 64 rows of w_hi
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t adv = (uint64_t)(ks * 2);
-                  tc::umma_f16_pair(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
-                  tc::umma_f16_pair(d_corr, al + adv, bx + adv, idesc, 1);
-                }
-                tc::umma_commit_pair(&w_empty[slot], 3);
-              } else {
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  const uint64_t adv = (uint64_t)(ks * 2);
-                  tc::umma_f16(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
-                  tc::umma_f16(d_corr, al + adv, bh + adv, idesc, 1);
-                }
-                tc::umma_commit(&w_empty[slot]);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                tc::umma_f16(d_main, ah + adv, bh + adv, idesc2, (c | ks) != 0);
+                tc::umma_f16(d_corr, al + adv, bh + adv, idesc, 1);
               }
+              tc::umma_commit(&w_empty[slot]);
             }
           }
-          if (PAIR) tc::umma_commit_pair(d_full, 3);
-          else tc::umma_commit(d_full);
+          tc::umma_commit(d_full);
         }
     }
   } else {
@@ -1781,8 +1676,7 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) tc::mbar_arrive_cluster(x_full_ldr);
-        else tc::mbar_arrive(x_full);
+        tc::mbar_arrive(x_full);
       }
 
       // ---- residual layers: thread = (row, 64 columns = K-chunks 2cq, 2cq+1 of the next layer's operand)
@@ -1831,8 +1725,7 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) tc::mbar_arrive_cluster(x_full_ldr);
-          else tc::mbar_arrive(x_full);
+          tc::mbar_arrive(x_full);
         }
       }
       // ---- last layer: Z = act(D + b), 128 columns; each (row, quarter) thread takes 32 of them
@@ -1922,17 +1815,15 @@ __device__ __forceinline__ void fc_readout_tc_body(const FcTcArgs& p) {
     }
   }
   tc::tc_fence_before();
-  if (PAIR) tc::cluster_sync();
-  else __syncthreads();
+  __syncthreads();
   if (warp == 1) {
-    if (PAIR) tc::tmem_dealloc_pair<512>(tmem_base);
-    else tc::tmem_dealloc<512>(tmem_base);
+    tc::tmem_dealloc<512>(tmem_base);
   }
 }
 
 template <int ACT>
 __global__ void __launch_bounds__(FTC_THREADS, 1) fc_readout_tc_kernel(const FcTcArgs p) {
-  fc_readout_tc_body<ACT, false>(p);
+  fc_readout_tc_body<ACT>(p);
 }
 
 }  // namespace nmr
