@@ -13,5 +13,6 @@ from .library import (check_peaks, load_baseline, load_embeddings, load_model, l
                       universe2graph)
 from .graph import Universe, batch_graphs, build_graph, read_pdb  # noqa: F401
 from .evalstruct import eval_struct  # noqa: F401
+from .batchstream import BatchStream  # noqa: F401
 
 custom_objects = {c.__name__: c for c in (MPLayer, RBFExpansion, EdgeFCBlock, MPBlock, FCBlock)}

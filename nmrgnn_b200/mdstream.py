@@ -71,7 +71,9 @@ class FrameStream:
             self.h_pos = [torch.zeros((B * n, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
             self.h_peaks = [torch.zeros(B * n, dtype=torch.float32).pin_memory() for _ in range(2)]
             self.compute = torch.cuda.Stream(device=self.dev)
-            self.copy = torch.cuda.Stream(device=self.dev)
+            self.copy = torch.cuda.Stream(device=self.dev)      # uploads
+            self.down = torch.cuda.Stream(device=self.dev)      # downloads (separate: a download waits for its batch's kernels
+            #                                                   # and must not hold back the next batch's upload behind it)
         self.offsets = np.arange(B + 1, dtype=np.int64) * n
         self.graphs = [None, None]           # one captured graph per (positions, peaks) buffer pair
         self.graph_captured = False
@@ -164,10 +166,10 @@ class FrameStream:
             with torch.cuda.stream(self.compute):
                 self._step(i & 1)
                 k_done[i & 1].record(self.compute)
-            with torch.cuda.stream(self.copy):
-                self.copy.wait_event(k_done[i & 1])
+            with torch.cuda.stream(self.down):
+                self.down.wait_event(k_done[i & 1])
                 self.h_peaks[i & 1].copy_(self.d_peaks[i & 1], non_blocking=True)
-                down_done[i & 1].record(self.copy)
+                down_done[i & 1].record(self.down)
         ev1.record(self.compute)
         for i in range(max(0, len(mine) - 2), len(mine)):
             row = collect(i, row)

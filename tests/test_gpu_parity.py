@@ -159,6 +159,26 @@ def test_calls_on_different_streams_are_serialised(model):
         assert np.array_equal(oa.cpu().numpy(), ya) and np.array_equal(ob.cpu().numpy(), yb) and np.array_equal(yh, ya)
 
 
+def test_batch_stream_equals_synchronous_calls(model):
+    """BatchStream (upload of batch i + 1 / download of batch i - 1 overlapped with the kernels of batch i) returns the
+    bits of the synchronous host-buffer call for every batch of a sequence of different sizes; a bad neighbour index in
+    one batch still raises."""
+    from nmrgnn_b200 import BatchStream, workloads
+    batches = [workloads.protein_batch(g, first_seed=s)[:4] for g, s in ((3, 0), (1, 9), (4, 20), (2, 31), (3, 40))]
+    ref = [model(b) for b in batches]
+    bs = BatchStream(model, max(b[0].shape[0] for b in batches), 16)
+    for pinned in (False, True):
+        res = bs.run([BatchStream.pin(b) if pinned else b for b in batches])
+        assert len(res["peaks"]) == len(batches)
+        for y, r in zip(res["peaks"], ref):
+            assert np.array_equal(y, r)
+    bad = [np.array(x) for x in batches[1]]
+    bad[1][5, 3] = 10 ** 7
+    with pytest.raises(IndexError):
+        bs.run([batches[0], tuple(bad), batches[2]])
+    assert np.array_equal(bs.run([batches[0]])["peaks"][0], ref[0])      # the stream stays usable
+
+
 def test_device_tensors_equal_host_path(model):
     import torch
     g = load_golden("prot300")
