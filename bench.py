@@ -141,13 +141,16 @@ class ClockSampler:
 
 def make_workload(rank: int, world: int, config: int, graphs_total: int = 0):
     """This rank's graphs of the selected configuration (a rank only generates the graphs it owns).
-    config 2: weak scaling, seeds rank*64 .. rank*64+63.  configs 3 / 4: the G graphs with seeds 0..G-1 assigned to
-    ranks by the greedy atom-count balance of nmrgnn_b200.sharding.ShardPlan."""
+    config 2: weak scaling, 64 graphs per GPU: the 64 N graphs with seeds 0 .. 64 N - 1; configs 3 / 4: the G graphs with
+    seeds 0..G-1.  In every case the graphs are assigned to the ranks by the greedy atom-count balance of
+    nmrgnn_b200.sharding.ShardPlan (at N = 1 config 2 is exactly seeds 0..63)."""
     from nmrgnn_b200 import workloads
     from nmrgnn_b200.graph import batch_graphs
     from nmrgnn_b200.sharding import ShardPlan
     if config == 2 and graphs_total <= 0:
-        return workloads.protein_batch(GRAPHS_PER_GPU, first_seed=rank * GRAPHS_PER_GPU, neighbor_number=K_NEIGH)
+        if world == 1:
+            return workloads.protein_batch(GRAPHS_PER_GPU, first_seed=0, neighbor_number=K_NEIGH)
+        graphs_total = GRAPHS_PER_GPU * world
     if config == 3:
         total = graphs_total or 1024
         sizes = np.array([workloads.small_molecule_graph(s)[0].shape[0] for s in range(total)], np.int64) if world > 1 else None
@@ -163,7 +166,8 @@ def make_workload(rank: int, world: int, config: int, graphs_total: int = 0):
 
 
 WORKLOAD_TEXT = {
-    2: "config[1]: batch of {g} synthetic protein graphs (~2500 atoms, 16-wide nlist), fp32, pretrained weights, per GPU",
+    2: "config[1]: batch of {g} synthetic protein graphs (~2500 atoms, 16-wide nlist), fp32, pretrained weights, per GPU "
+       "(N GPUs: the 64 N graphs with seeds 0 .. 64 N - 1, sharded by the library's greedy atom-count balance)",
     3: "config[2]: batch of {g} small-molecule graphs (~40 atoms, 8-wide nlist), fp32, sharded by graph over {n} GPU(s)",
     4: "config[3]: batch of {g} synthetic protein graphs sharded by graph over {n} GPU(s), peaks reassembled on every rank",
     5: "config[4]: MD trajectory stream, 108M.pdb x {g} jittered frames, graph build + forward per frame batch, "
