@@ -199,6 +199,12 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
  *   "knn_cells" = 0: nmrgnn_knn_graph searches every atom of the graph per query (brute force) instead of the cell list
  *                  (default 1; identical output);
+ *   "mp_single_acc" = 1: MP layers on the single-accumulator kernel: main and correction products accumulate into ONE
+ *                  256-column accumulator, so tensor memory holds two sets and the epilogue of a tile runs under the next
+ *                  tile's MMAs (the MMA warp no longer waits for the drain); 7 % faster MP layers, but 144 instead of 48
+ *                  truncating accumulation steps per output: max error on config 2 0.83 instead of 0.53 of the tolerance
+ *                  (default 0);
+ *   "mp_pos_comp1_x100" = v: slope of that kernel's position-dependent compensation (default 55);
  *   "mp_nsplit" = 1: run the MP layers on column-split CTA pairs (kernels_mp_nsplit.cuh: two CTAs of a cluster share one
  *                  128-atom tile, each owns 128 output columns and gathers 64 rows; double-buffered accumulators) --
  *                  bit-identical results, measured slower than the one-CTA kernel (0.45 vs 0.37 ms); default 0;

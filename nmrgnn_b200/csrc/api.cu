@@ -89,6 +89,12 @@ struct nmrgnn_handle {
   float edge_pos_c = 0.3f;                // measured optimum for the edge MLP (profiles/r02_parity.md)
   std::vector<std::vector<float>> fc_w_host;   // the node MLP's weights, for the same reason
   float fc_pos_c = 0.5f;                // the same for the node MLP's 16-instruction chains (pack_fc_images)
+  // single-accumulator form of the MP layers (kernels_tc.cuh mp_layer_tc1_kernel): its own images, scales and constants
+  bool mp_one = false;                  // option "mp_single_acc"
+  std::vector<const uint8_t*> mp_img1;  // per layer: W' x 2^s pre-scaled, lo image NOT scaled by 2^11
+  std::vector<float> mp_wscale_inv;     // per layer 2^-s
+  std::vector<float> mp_corr1;          // residual constants of this form (calibrate_mp)
+  float mp_pos_c1 = 0.55f;              // slope of its position-dependent compensation (144-instruction chains)
   float mp_pos_c = 0.5f;                // position-dependent compensation slope c' (x 2^-24), see pack_mp_images
   DevBuf rec, hmaxA, hmaxB;
   // round-toward-zero compensation of the tcgen05 accumulation (DESIGN.md "Accumulation model"):
@@ -210,17 +216,18 @@ void pack_sw64(const float* W, int K, int ldw, int n0, int rows_valid, int rows_
 // `gain(k)` (optional) is a relative weight correction g_k << 2^-11 folded into the lo image only:
 // hi = fp16(w), lo = fp16((w (1 + g_k) - hi) * 2^11) -- the position-dependent compensation of the MP layers.
 template <typename Get, typename Gain>
-void pack_sw64_f16(Get get, Gain gain, int K, int rows_valid, int rows_tile, std::vector<uint8_t>& out) {
+void pack_sw64_f16(Get get, Gain gain, int K, int rows_valid, int rows_tile, std::vector<uint8_t>& out,
+                   double w_scale = 1.0, double lo_scale = (double)tc::LO_SCALE) {
   const int chunks = K / tc::HK;
   const size_t tile = (size_t)rows_tile * 64;
   out.assign((size_t)chunks * 2 * tile, 0);
   for (int c = 0; c < chunks; ++c)
     for (int n = 0; n < rows_valid; ++n)
       for (int kk = 0; kk < tc::HK; ++kk) {
-        const float w = get(c * tc::HK + kk, n);
-        const __half hi = __float2half_rn(w);
-        const double wg = (double)w * (1.0 + gain(c * tc::HK + kk));
-        const __half lo = __float2half_rn((float)((wg - (double)__half2float(hi)) * (double)tc::LO_SCALE));
+        const double ws = (double)get(c * tc::HK + kk, n) * w_scale;      // (w_scale is a power of two: exact)
+        const __half hi = __float2half_rn((float)ws);
+        const double wg = ws * (1.0 + gain(c * tc::HK + kk));
+        const __half lo = __float2half_rn((float)((wg - (double)__half2float(hi)) * lo_scale));
         const size_t off = (size_t)n * 64 + ((((size_t)kk >> 3) ^ (((size_t)n >> 1) & 3)) << 4) + (((size_t)kk & 7) << 1);
         std::memcpy(out.data() + (size_t)c * 2 * tile + off, &hi, 2);
         std::memcpy(out.data() + (size_t)c * 2 * tile + tile + off, &lo, 2);
@@ -687,12 +694,14 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.hmax_out = hmax_out;
   a.rec = rec;
   a.inv_degree = invdeg;
-  a.Wimg = h->mp_img[layer];
+  const bool one = h->mp_one && h->mp_nseg == 1 && !h->mp_nsplit;
+  a.Wimg = one ? h->mp_img1[layer] : h->mp_img[layer];
   a.n_atoms = n;
   a.K = K;
   a.E = h->d.edge_features;
   a.act = h->d.mp_activation;
-  a.corr = (h->compensate && !raw) ? h->mp_corr[layer] : 1.0f;
+  a.corr = (h->compensate && !raw) ? (one ? h->mp_corr1[layer] : h->mp_corr[layer]) : 1.0f;
+  if (one) a.corr *= h->mp_wscale_inv[layer];        // exact: a power of two
   a.raw = raw;
   a.swz = rec_swizzled(K) ? 1 : 0;
   a.nseg = h->mp_nseg;
@@ -704,6 +713,8 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   if (nsplit) {
     const int64_t pairs = std::min<int64_t>(tiles, h->num_sms / 2);
     ACT_DISPATCH(a.act, mp_layer_np_kernel, (unsigned)(2 * pairs), MNP_THREADS, MNP_SMEM, s, a);
+  } else if (one) {
+    ACT_DISPATCH(a.act, mp_layer_tc1_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   } else if (a.nseg > 1) ACT_DISPATCH(a.act, mp_layer_tc_seg_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   else ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   h->launches++;
@@ -821,6 +832,37 @@ int pack_mp_images(nmrgnn_handle* h) {
       CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->mp_img[l]), img.data(), img.size(), cudaMemcpyHostToDevice));
     }
   }
+  // ---- single-accumulator form: every one of the 6 instructions of a (pass, n) chunk -- main ks0, lo*hi ks0, main ks1,
+  // lo*hi ks1, hi*lo ks0, hi*lo ks1 -- truncates the one accumulator, so a main product at position p of the 6*8*E
+  // instructions is truncated 6*8*E - p times.  W' is pre-scaled by 2^s (s from max|w|: the unscaled lo image must stay
+  // in the normal fp16 range); 2^-s goes into the epilogue's output scale.
+  const bool fresh1 = h->mp_img1.empty();
+  if (fresh1) {
+    h->mp_img1.assign(L, nullptr);
+    h->mp_wscale_inv.assign(L, 1.0f);
+  }
+  const int n_instr1 = 6 * (F / 32) * E;
+  const double cpos1 = h->compensate ? (double)h->mp_pos_c1 / 16777216.0 : 0.0;
+  for (int l = 0; l < L; ++l) {
+    const float* src = h->mp_w_host[l].data();
+    const float wmax = max_abs(src, (size_t)F * F * E);
+    int sexp = 0;
+    while (sexp < 24 && wmax * std::ldexp(1.0f, sexp + 1) <= 32768.0f) ++sexp;
+    h->mp_wscale_inv[l] = std::ldexp(1.0f, -sexp);
+    pack_sw64_f16(
+        [&](int kg, int m) {
+          const int qch = kg / 32, ll = kg % 32, ps = qch / E, n = qch % E;
+          return src[((size_t)(32 * ps + ll) * F + m) * E + n];
+        },
+        [&](int kg) { return cpos1 * (double)(n_instr1 - (6 * (kg / 32) + 2 * ((kg % 32) / 16))); }, F * E, F, F, img,
+        std::ldexp(1.0, sexp), 1.0);
+    if (fresh1) {
+      if (int rc = upload_bytes(h, img.data(), img.size(), &h->mp_img1[l])) return rc;
+    } else {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->mp_img1[l]), img.data(), img.size(), cudaMemcpyHostToDevice));
+    }
+  }
   return NMRGNN_OK;
 }
 
@@ -925,10 +967,28 @@ int calibrate_mp(nmrgnn_handle* h) {
   if ((rc = launch_pack_rec(h, s, (const int32_t*)h->nlist.p, (const float*)h->efeat.p, (float4*)h->rec.p,
                             (int64_t)N * K, N, K)))
     return rc;
+  std::vector<float> df((size_t)N * F), dt((size_t)N * F);
+  const bool saved_one = h->mp_one, saved_nsplit = h->mp_nsplit;
+  const int saved_nseg = h->mp_nseg;
+  h->mp_corr1.assign(h->d.n_mp, 1.0f);
+  struct Restore {
+    nmrgnn_handle* h;
+    bool one, nsplit;
+    int nseg;
+    ~Restore() {
+      h->mp_one = one;
+      h->mp_nsplit = nsplit;
+      h->mp_nseg = nseg;
+    }
+  } restore{h, saved_one, saved_nsplit, saved_nseg};
+  // two passes: the two-accumulator kernel (with the current chain segmentation), then the single-accumulator kernel
+  for (int variant = 0; variant < 2; ++variant) {
+  h->mp_one = variant == 1;
+  h->mp_nsplit = false;
+  if (variant == 1) h->mp_nseg = 1;
   float* ha = (float*)h->hA.p;
   float* hb = (float*)h->hB.p;
   if ((rc = launch_embed(h, s, (const float*)h->atoms.p, N, ha))) return rc;
-  std::vector<float> df((size_t)N * F), dt((size_t)N * F);
   for (int l = 0; l < h->d.n_mp; ++l) {
     if ((rc = launch_mp(h, s, l, ha, (const int32_t*)h->nlist.p, (const float*)h->efeat.p, (const float*)h->invdeg.p, N,
                         K, (float*)h->tmp_in.p, 1)))
@@ -961,8 +1021,9 @@ int calibrate_mp(nmrgnn_handle* h) {
     double c = den > 0.0 ? -num / den : 0.0;
     if (!(c == c)) c = 0.0;                  // NaN
     c = std::fmin(std::fmax(c, -256.0 / 16777216.0), 256.0 / 16777216.0);
-    h->mp_corr[l] = (float)(1.0 + c);
+    (variant == 1 ? h->mp_corr1 : h->mp_corr)[l] = (float)(1.0 + c);
     std::swap(ha, hb);
+  }
   }
   CUDA_TRY(h, cudaGetLastError());
   return nmrgnn_synchronize(h, nullptr);
@@ -1192,6 +1253,11 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(pack_mp_images(h));
     ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
     ACT_SET_SMEM(mp_layer_tc_seg_kernel, MTC_SMEM);
+    ACT_SET_SMEM(mp_layer_tc1_kernel, MTC_SMEM);
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc1_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc1_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc1_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc1_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     ACT_SET_SMEM(mp_layer_np_kernel, MNP_SMEM);
     // 162 KB of shared memory: the 164 KB configuration leaves 92 KB of L1 for the gathers
     CUDA_RC(cudaFuncSetAttribute(mp_layer_np_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
@@ -1662,7 +1728,8 @@ int nmrgnn_tc_compensation(nmrgnn_handle* h, float* c_ulp, int cap) {
   const int n = (int)h->mp_corr.size();
   if (cap < n + 1) return fail(h, NMRGNN_ERR_BAD_DIMS, "need room for %d values", n + 1);
   c_ulp[0] = (h->edge_rz - 1.0f) * 16777216.0f;
-  for (int l = 0; l < n; ++l) c_ulp[1 + l] = (h->mp_corr[l] - 1.0f) * 16777216.0f;
+  const bool one = h->mp_one && h->mp_nseg == 1 && !h->mp_nsplit && (int)h->mp_corr1.size() == n;
+  for (int l = 0; l < n; ++l) c_ulp[1 + l] = ((one ? h->mp_corr1[l] : h->mp_corr[l]) - 1.0f) * 16777216.0f;
   return n + 1;
 }
 
@@ -1730,6 +1797,19 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "knn_cells") == 0) {
     h->knn_cells_on = value != 0;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_single_acc") == 0) {
+    h->mp_one = value != 0;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_pos_comp1_x100") == 0) {  // slope of the single-accumulator form's position-dependent compensation
+    if (value < 0 || value > 400) return fail(h, NMRGNN_ERR_BAD_DIMS, "mp_pos_comp1_x100 must be in 0..400");
+    h->mp_pos_c1 = (float)value / 100.0f;
+    if (h->mp_tc_ok) {
+      if (int rc = pack_mp_images(h)) return rc;
+      return calibrate_mp(h);
+    }
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_nsplit") == 0) {

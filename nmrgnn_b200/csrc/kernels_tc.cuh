@@ -920,8 +920,9 @@ constexpr int MTC_KMAX = 16;
 // feature pass (~38 KB unique per tile) then mostly hit L1.
 constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * MTC_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 static_assert(MTC_SMEM + 1024 <= 196 * 1024, "MP tensor-core kernel no longer fits the 196 KB shared-memory configuration");
-template <int ACT, bool SEG>
+template <int ACT, bool SEG, bool ONE>
 __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
+  static_assert(!(SEG && ONE), "chain segments drain per segment: not combined with the single-accumulator form");
   constexpr int BRING = MTC_BRING;
   constexpr int BSLOT = MTC_BSLOT;
   constexpr bool SPLIT = true;      // one slot = one image (hi or lo) of a (pass, n) chunk
@@ -940,9 +941,9 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   uint64_t* b_empty = b_full + BRING;
   uint64_t* rec_full = b_empty + BRING;
   uint64_t* rec_empty = rec_full + 1;
-  uint64_t* d_full = rec_empty + 1;
-  uint64_t* d_empty = d_full + 1;
-  uint64_t* sc_full = d_empty + 1;    // [2]
+  uint64_t* d_full = rec_empty + 1;   // [2] (the second one: single-accumulator form, accumulator set 1)
+  uint64_t* d_empty = d_full + 2;     // [2]
+  uint64_t* sc_full = d_empty + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sc_full + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -958,8 +959,10 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     }
     tc::mbar_init(rec_full, 1);
     tc::mbar_init(rec_empty, 8);
-    tc::mbar_init(d_full, 1);
-    tc::mbar_init(d_empty, 4);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&d_full[i], 1);
+      tc::mbar_init(&d_empty[i], 4);
+    }
     tc::mbar_fence_init();
   }
   if (warp == 1) {
@@ -1030,12 +1033,22 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
       const long long k0 = clock64();
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
         for (int ps = 0; ps < MTC_PASSES; ++ps, ++pass) {
-          if (ps % seg_passes == 0) {            // a new accumulation chain: the epilogue has drained the previous one
+          if (ONE) {
+            if (ps == 0) {                       // this accumulator set was drained two tiles ago
+              if (p.dbg) c0 = clock64();
+              tc::mbar_wait(&d_empty[t & 1], ((t >> 1) & 1) ^ 1);
+              if (p.dbg) w_d += clock64() - c0;
+              tc::tc_fence_after();
+            }
+          } else if (ps % seg_passes == 0) {     // a new accumulation chain: the epilogue has drained the previous one
             if (p.dbg) c0 = clock64();
             tc::mbar_wait(d_empty, (dph & 1) ^ 1);
             if (p.dbg) w_d += clock64() - c0;
             tc::tc_fence_after();
           }
+          // single-accumulator form: main and correction products share ONE accumulator (256 columns), so tensor memory
+          // holds two sets and tile t + 1 accumulates while tile t is drained
+          const uint32_t dm = ONE ? tmem_base + (t & 1u) * 256u : d_main, dc = ONE ? dm : d_corr;
           const uint32_t st = pass % AST;
           if (p.dbg) c0 = clock64();
           tc::mbar_wait(&a_full[st], (pass / AST) & 1);
@@ -1057,9 +1070,9 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
               const uint64_t adv = (uint64_t)(ks * 2);
               // main restarts with every chain; the correction accumulator (its truncation is scaled by 2^-11)
               // runs through the whole tile and is read once, by the last chain's epilogue
-              const uint32_t acc = ((ps % seg_passes) | n | ks) != 0, acc_c = (ps | n | ks) != 0;
-              tc::umma_f16(d_main, ah + adv, bh + adv, idesc, acc);
-              tc::umma_f16(d_corr, al + adv, bh + adv, idesc, acc_c);
+              const uint32_t acc = ((ps % seg_passes) | n | ks) != 0, acc_c = ONE ? 1u : (uint32_t)((ps | n | ks) != 0);
+              tc::umma_f16(dm, ah + adv, bh + adv, idesc, acc);
+              tc::umma_f16(dc, al + adv, bh + adv, idesc, acc_c);
             }
             uint64_t bl;
             if (SPLIT) {     // the lo image is the next slot of the ring
@@ -1078,12 +1091,14 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
-              tc::umma_f16(d_corr, ah + adv, bl + adv, idesc, 1);
+              tc::umma_f16(dc, ah + adv, bl + adv, idesc, 1);
             }
             tc::umma_commit(&b_empty[slot]);
           }
           tc::umma_commit(&a_empty[st]);
-          if ((ps + 1) % seg_passes == 0) {      // chain complete: hand the accumulators to the epilogue
+          if (ONE) {
+            if (ps + 1 == MTC_PASSES) tc::umma_commit(&d_full[t & 1]);
+          } else if ((ps + 1) % seg_passes == 0) {      // chain complete: hand the accumulators to the epilogue
             tc::umma_commit(d_full);
             ++dph;
           }
@@ -1110,16 +1125,22 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t t_corr = t_main + 256u;
     uint32_t t = 0, dph = 0;
+    float osc_one = 0.0f;          // single-accumulator form: this tile's output scale, fetched one tile ahead (see below)
+    if (ONE && tile_first < tile_end) {
+      tc::mbar_wait(&sc_full[0], 0);
+      osc_one = oscale[row] * p.corr;
+    }
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
       const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
-      tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
+      if (!ONE) tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
       float hm[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) hm[k] = 0.0f;
       if constexpr (!SEG) {
         // one accumulation chain per tile (the default): drain, compensate, activate, add the residual
-        const float osc = oscale[(t & 1) * 128 + row] * p.corr;   // (1 + c) once per row: one chain
+        const float osc = ONE ? osc_one : oscale[(t & 1) * 128 + row] * p.corr;   // (1 + c) once per row: one chain
+        const uint32_t t_set = t_main + (ONE ? (t & 1u) * 256u : 0u);
         // rows grow .. grow+7 of this group, clamped for the loads (stores are predicated)
         const float* hin = p.h_in + (rows > 0 ? a0 + min(grow, rows - 1) : 0) * 256 + gi * 4;
         float* hout = p.h_out + (a0 + grow) * 256 + gi * 4;
@@ -1128,21 +1149,41 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         float4 res[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) res[k] = p.raw ? make_float4(0.f, 0.f, 0.f, 0.f) : tc::ldg128(hin + min(k, rlast) * 256);
-        tc::mbar_wait(d_full, dph & 1);
-        ++dph;
+        if (ONE) {
+          tc::mbar_wait(&d_full[t & 1], (t >> 1) & 1);
+        } else {
+          tc::mbar_wait(d_full, dph & 1);
+          ++dph;
+        }
         const long long e0 = p.dbg ? clock64() : 0;
         tc::tc_fence_after();
+        if (ONE) {
+          // The next tile's scale is picked up BEFORE this accumulator set is handed back: the producers can overwrite
+          // that scale buffer (for tile t + 3) only after the MMAs of tile t + 2 have started, which wait for this set.
+          // (It was written long ago: the producers finished tile t before its MMAs completed.)
+          if (tile + tile_step < tile_end) {
+            tc::mbar_wait(&sc_full[(t + 1) & 1], ((t + 1) >> 1) & 1);
+            osc_one = oscale[((t + 1) & 1) * 128 + row] * p.corr;
+          }
+        }
 #pragma unroll 1
         for (int cc = 0; cc < 8; ++cc) {
           float4 x[8];
           {
             float v[16];
-            tc::tmem_ld16_combined(t_main + cc * 32, t_corr + cc * 32, v);
+            if (ONE) tc::tmem_ld16(t_set + cc * 32, v);
+            else tc::tmem_ld16_combined(t_main + cc * 32, t_corr + cc * 32, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
-            tc::tmem_ld16_combined(t_main + cc * 32 + 16, t_corr + cc * 32 + 16, v);
+            if (ONE) tc::tmem_ld16(t_set + cc * 32 + 16, v);
+            else tc::tmem_ld16_combined(t_main + cc * 32 + 16, t_corr + cc * 32 + 16, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[4 + j] = make_float4(v[4 * j] * osc, v[4 * j + 1] * osc, v[4 * j + 2] * osc, v[4 * j + 3] * osc);
+          }
+          if (ONE && cc == 7) {    // every accumulator of the set is in registers: the MMAs of tile t + 2 may overwrite it
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&d_empty[t & 1]);
           }
           // 8 x 8 transpose of float4 inside the 8-lane group (3 butterfly stages)
 #pragma unroll
@@ -1181,7 +1222,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         }
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !ONE) {
           tc::mbar_arrive(d_empty);
         }
         if (p.dbg && warp == 4 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 4), (unsigned long long)(clock64() - e0));
@@ -1449,8 +1490,13 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           for (int n = 0; n < 3; ++n) {
             if (n < E) {
               uint2 hi, lo;
-              tc::split2_f16(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
-              tc::split2_f16(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
+              if (ONE) {       // lo = x - hi, not scaled by 2^11: it meets the main products in the same accumulator
+                tc::split2_f16_plain(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
+                tc::split2_f16_plain(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
+              } else {
+                tc::split2_f16(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
+                tc::split2_f16(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
+              }
               tc::sts64(ab + n * 16384 + off, hi.x, hi.y);
               tc::sts64(ab + n * 16384 + 8192 + off, lo.x, lo.y);
             }
@@ -1475,12 +1521,21 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
 
 template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcArgs p) {
-  mp_layer_tc_body<ACT, false>(p);
+  mp_layer_tc_body<ACT, false, false>(p);
+}
+// Single-accumulator form (option "mp_single_acc"): main and correction products accumulate into ONE 256-column
+// accumulator (the lo operand images are not scaled by 2^11; W' is pre-scaled by a power of two so that its lo image
+// stays in the normal fp16 range), so tensor memory holds two accumulator sets and the epilogue of tile t runs under
+// the MMAs of tile t + 1.  Price: 144 instead of 48 round-toward-zero steps at full magnitude per output (the
+// position-dependent compensation follows the 144-instruction order), error at the level of the exact-FP32 kernels.
+template <int ACT>
+__global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc1_kernel(const MpTcArgs p) {
+  mp_layer_tc_body<ACT, false, true>(p);
 }
 // the same with the K loop cut into p.nseg accumulation chains (option "mp_chain_segments" > 1)
 template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_seg_kernel(const MpTcArgs p) {
-  mp_layer_tc_body<ACT, true>(p);
+  mp_layer_tc_body<ACT, true, false>(p);
 }
 
 }  // namespace nmr

@@ -94,6 +94,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_t<4000>(bar, parity); }
 
+
 // One lane of a fully converged warp.  Issuing tcgen05.mma / commit under `if (elect_one())` inside warp-uniform
 // control flow lets the compiler keep descriptors and addresses in uniform registers; issuing them from an
 // `if (lane == 0)` region instead makes it wrap every UTCHMMA in an elect / R2UR.BROADCAST / branch "waterfall"
@@ -390,6 +391,14 @@ __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uin
   const __half2 h = __floats2half2_rn(x0, x1);
   const float2 hf = __half22float2(h);
   const __half2 l = __floats2half2_rn((x0 - hf.x) * LO_SCALE, (x1 - hf.y) * LO_SCALE);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// the same without the 2^11 scaling of lo (single-accumulator form of the MP layer)
+__device__ __forceinline__ void split2_f16_plain(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }

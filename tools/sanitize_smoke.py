@@ -28,7 +28,8 @@ def main():
                             ("tcgen05 + edge table", {"tc_min_atoms": 0}),
                             ("tcgen05 + edge MLP", {"tc_min_atoms": 0, "edge_table": 0}),
                             ("tcgen05, column-split MP pairs", {"tc_min_atoms": 0, "mp_nsplit": 1}),
-                            ("tcgen05, 2 chain segments", {"tc_min_atoms": 0, "mp_chain_segments": 2})):
+                            ("tcgen05, 2 chain segments", {"tc_min_atoms": 0, "mp_chain_segments": 2}),
+                            ("tcgen05, single accumulator", {"tc_min_atoms": 0, "mp_single_acc": 1})):
             for k, v in opts.items():
                 h.set_option(k, v)
             y = m(graph)
