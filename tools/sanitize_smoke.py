@@ -36,6 +36,21 @@ def main():
             print(f"{name:14s} {label:34s} path {h.compute_path:40s} tol_ratio {tol_ratio(y, g['peaks_f64']):.3f}", flush=True)
             for k in opts:
                 h.set_option(k, {"tc_min_atoms": 1024, "edge_table": 1, "mp_chain_segments": 1}.get(k, 0))
+    # GPU graph builder: cell list and brute force on a 900-atom fragment, two graphs in one call
+    from nmrgnn_b200 import _capi
+    from conftest import GOLDEN
+    with np.load(os.path.join(GOLDEN, "g108m_structure.npz")) as z:
+        pos = np.ascontiguousarray(z["positions_A"].astype(np.float32)[:900] / np.float32(10))
+    pos2 = np.ascontiguousarray(np.concatenate([pos, pos[:300] + 1.0], 0))
+    offs = np.array([0, 900, 1200], np.int64)
+    res = []
+    for mode in (1, 0):
+        h.set_option("knn_cells", mode)
+        nl, ed, inv = np.empty((1200, 16), np.int32), np.empty((1200, 16), np.float32), np.empty(1200, np.float32)
+        h.knn_graph(pos2, offs, 1200, 2, 16, 0.0, nl, ed, inv, _capi.MEM_HOST)
+        res.append((nl, ed, inv))
+    h.set_option("knn_cells", 1)
+    print("knn graph builder: cell list == brute force:", all(np.array_equal(a, b) for a, b in zip(*res)), flush=True)
     m.close()
 
 
