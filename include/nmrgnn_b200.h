@@ -199,6 +199,15 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
  *   "knn_cells" = 0: nmrgnn_knn_graph searches every atom of the graph per query (brute force) instead of the cell list
  *                  (default 1; identical output);
+ *   "fc_pipe" = 0: node MLP + readout on the round-1 kernel (MMA and epilogue phases alternate on the resident tile; main
+ *                  and correction products in separate accumulators) instead of the layer-pipelined kernel
+ *                  (kernels_fc_pipe.cuh, default 1: one accumulator per layer, two sets in tensor memory, layer l + 1
+ *                  accumulates K-chunk by K-chunk under the epilogue of layer l, the next tile is staged by its own
+ *                  warps, the readout is formed from registers);
+ *   "fc_pos_comp1_x100" = v: slope of the pipelined kernel's position-dependent compensation (48-instruction chains,
+ *                  default 50);
+ *   "fc_role_counters" = 1 / 2 / 0: diagnostics -- arm / print / disarm per-CTA cycle counters of the pipelined node-MLP
+ *                  kernel's warp roles;
  *   "mp_single_acc" = 1: MP layers on the single-accumulator kernel: main and correction products accumulate into ONE
  *                  256-column accumulator, so tensor memory holds two sets and the epilogue of a tile runs under the next
  *                  tile's MMAs (the MMA warp no longer waits for the drain); 7 % faster MP layers, but 144 instead of 48

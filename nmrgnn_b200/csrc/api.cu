@@ -18,6 +18,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_mp_nsplit.cuh"
+#include "kernels_fc_pipe.cuh"
 #include "knn.cuh"
 #include "edge_table.cuh"
 #include "peer_gather.cuh"
@@ -106,6 +107,13 @@ struct nmrgnn_handle {
   const float* fc_bias = nullptr;       // [n_fc][256]
   float fc_gain[MAX_DENSE], fc_offs[MAX_DENSE];
   float fc_rz = 1.0f;
+  // layer-pipelined single-accumulator form of the node MLP (kernels_fc_pipe.cuh): its own images, scales and bounds
+  bool fc_pipe = true;                  // option "fc_pipe"
+  const uint8_t* fc_img1 = nullptr;     // per layer [8 chunks][hi 16384 | lo 16384] (last: [hi 8192 | lo 8192]), W x 2^s, lo unscaled
+  float fc_wsinv[MAX_DENSE];            // per layer 2^-s
+  float fc_g1[MAX_DENSE], fc_o1[MAX_DENSE];   // one-layer growth bound: max|x_{l+1}| <= g max|x_l| + o
+  float fc_pos_c1 = 0.5f;               // slope of its position-dependent compensation (48-instruction chains)
+  long long* fc_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last pipelined node-MLP launch
   bool compensate = true;
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
@@ -721,8 +729,9 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   return NMRGNN_OK;
 }
 
+// hmax: max |nodes row| per atom if the caller has it ([n][2] partial maxima if hmax_pair), else NULL
 int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float* atoms, int64_t n, float* peaks,
-              float* fc_nodes) {
+              float* fc_nodes, const float* hmax = nullptr, int hmax_pair = 0) {
   if (n == 0) return NMRGNN_OK;
   if (!h->fast_path) {
     const int F = h->d.atom_features, F2 = F / 2, C = h->d.num_elem, L = h->d.n_fc;
@@ -743,6 +752,42 @@ int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float*
     }
     gen_readout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, atoms, h->out_W, h->out_b, h->peak_std, h->peak_avg,
                                                                   peaks, n, F2, C);
+    h->launches++;
+    return NMRGNN_OK;
+  }
+  if (h->fc_tc_ok && !h->force_ffma && h->fc_pipe && h->fc_img1 && h->d.num_elem <= FPI_CMAX) {
+    if (hmax == nullptr) {
+      if (int rc = ensure(h, h->hmaxA, 2 * (size_t)n * sizeof(float))) return rc;
+      if (int rc = launch_absmax(h, s, nodes, n, (float*)h->hmaxA.p)) return rc;
+      hmax = (const float*)h->hmaxA.p;
+      hmax_pair = 0;
+    }
+    FcPipeArgs t{};
+    t.nodes = nodes;
+    t.hmax = hmax;
+    t.hmax_pair = hmax_pair;
+    t.atoms = atoms;
+    t.peaks = peaks;
+    t.fc_nodes = fc_nodes;
+    t.n_atoms = n;
+    t.C = h->d.num_elem;
+    t.Wimg = h->fc_img1;
+    t.bias = h->fc_bias;
+    for (int i = 0; i < h->d.n_fc; ++i) {
+      t.g[i] = h->fc_g1[i];
+      t.o[i] = h->fc_o1[i];
+      t.wsinv[i] = h->fc_wsinv[i];
+    }
+    t.n_layers = h->d.n_fc;
+    t.act = h->d.fc_activation;
+    t.corr = h->compensate ? h->fc_rz : 1.0f;
+    t.Wo = h->out_W;
+    t.bo = h->out_b;
+    t.peak_std = h->peak_std;
+    t.peak_avg = h->peak_avg;
+    t.dbg = h->fc_dbg;
+    const int64_t tiles = (n + 127) / 128;
+    ACT_DISPATCH(t.act, fc_readout_pipe_kernel, grid_for(h, tiles, 1), FPI_THREADS, FPI_SMEM, s, t);
     h->launches++;
     return NMRGNN_OK;
   }
@@ -904,6 +949,34 @@ int pack_fc_images(nmrgnn_handle* h) {
     for (int c = 0; c < 8; ++c)
       for (int hf = 0; hf < halves; ++hf)
         all.insert(all.end(), half_img[hf].begin() + (size_t)c * 16384, half_img[hf].begin() + (size_t)(c + 1) * 16384);
+  }
+  // ---- layer-pipelined single-accumulator form (kernels_fc_pipe.cuh): per K = 16 step the instructions hi*hi, lo*hi,
+  // hi*lo all truncate the one accumulator, so the main product of step k (0..F/16-1) is truncated 3 (F/16 - k) times;
+  // W is pre-scaled by 2^s (s from max|w|: the unscaled lo image must stay in the normal fp16 range), 2^-s goes into
+  // the epilogue's output scale.  Every layer's image takes 16 slots of 16 KB (the last one uses 8).
+  {
+    const double cpos1 = h->compensate ? (double)h->fc_pos_c1 / 16777216.0 : 0.0;
+    const int n_instr1 = 3 * (F / 16);
+    std::vector<uint8_t> all1((size_t)n_fc * 16 * 16384, 0), img;
+    for (int i = 0; i < n_fc; ++i) {
+      const bool last = (i == n_fc - 1);
+      const int outw = last ? F / 2 : F;
+      const float* W = h->fc_w_host[i].data();
+      const float wmax = max_abs(W, (size_t)F * outw);
+      int sexp = 0;
+      while (sexp < 24 && wmax * std::ldexp(1.0f, sexp + 1) <= 32768.0f) ++sexp;
+      h->fc_wsinv[i] = std::ldexp(1.0f, -sexp);
+      pack_sw64_f16([&](int k, int n) { return W[(size_t)k * outw + n]; },
+                    [&](int k) { return cpos1 * (double)(n_instr1 - 3 * (k / 16)); }, F, outw, outw, img, std::ldexp(1.0, sexp),
+                    1.0);
+      std::memcpy(all1.data() + (size_t)i * 16 * 16384, img.data(), img.size());
+    }
+    if (!h->fc_img1) {
+      if (int rc = upload_bytes(h, all1.data(), all1.size(), &h->fc_img1)) return rc;
+    } else {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->fc_img1), all1.data(), all1.size(), cudaMemcpyHostToDevice));
+    }
   }
   if (!h->fc_img) return upload_bytes(h, all.data(), all.size(), &h->fc_img);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -1301,6 +1374,14 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
       h->fc_gain[i] = gain;
       h->fc_offs[i] = offs;
       const float ws = max_col_abs_sum(W, F, outw), bm = max_abs(b, outw);
+      // one-layer growth bound for the pipelined kernel (residual layers): |act(x W + b) + x| <= g max|x| + o
+      if (dims->fc_activation == ACT_TANH) {
+        h->fc_g1[i] = 1.0f;
+        h->fc_o1[i] = 1.0001f;
+      } else {
+        h->fc_g1[i] = (ws + 1.0f) * 1.0001f;
+        h->fc_o1[i] = (bm + (dims->fc_activation == ACT_SOFTPLUS ? 0.6931472f : 0.0f)) * 1.0001f;
+      }
       if (dims->fc_activation == ACT_TANH) {
         offs += 1.0f;
       } else {
@@ -1313,6 +1394,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     TRY_RC(upload(h, bias.data(), bias.size(), &h->fc_bias));
     h->fc_rz = 1.0f;
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
+    ACT_SET_SMEM(fc_readout_pipe_kernel, FPI_SMEM);
   }
   update_path(h);
 #undef TRY_RC
@@ -1510,6 +1592,8 @@ static int forward_core(nmrgnn_handle* h, const float* atoms, const int32_t* nli
     h->ev.resize(h->d.n_mp + 4);
     for (auto& e : h->ev) CUDA_TRY(h, cudaEventCreate(&e));
   }
+  const float* fc_hmax = nullptr;
+  int fc_hmax_pair = 0;
   int mk = 0;
   auto mark = [&]() {
     if (h->profile) cudaEventRecord(h->ev[mk++], s);
@@ -1541,6 +1625,8 @@ static int forward_core(nmrgnn_handle* h, const float* atoms, const int32_t* nli
       std::swap(ha, hb);
       std::swap(ma, mb);
     }
+    fc_hmax = ma;                  // the last MP epilogue (or the embedding) left max |h row| of the node MLP's input
+    fc_hmax_pair = m_pair;
   } else {
     for (int c = 0; c < n_chunks; ++c) {
       const int64_t a0 = c * chunk_atoms, na = std::min<int64_t>(chunk_atoms, n_atoms - a0);
@@ -1558,7 +1644,7 @@ static int forward_core(nmrgnn_handle* h, const float* atoms, const int32_t* nli
       std::swap(ha, hb);
     }
   }
-  if ((rc = launch_fc(h, s, ha, (const float*)d_atoms, n_atoms, (float*)d_peaks, nullptr))) return rc;
+  if ((rc = launch_fc(h, s, ha, (const float*)d_atoms, n_atoms, (float*)d_peaks, nullptr, fc_hmax, fc_hmax_pair))) return rc;
   mark();
   h->ev_valid = h->profile;
   if (dev_peaks == nullptr && (rc = io.finish(peaks, d_peaks, n_atoms * sizeof(float)))) return rc;
@@ -1797,6 +1883,39 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "knn_cells") == 0) {
     h->knn_cells_on = value != 0;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "fc_pipe") == 0) {
+    h->fc_pipe = value != 0;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "fc_pos_comp1_x100") == 0) {  // slope of the pipelined node MLP's position-dependent compensation
+    if (value < 0 || value > 400) return fail(h, NMRGNN_ERR_BAD_DIMS, "fc_pos_comp1_x100 must be in 0..400");
+    h->fc_pos_c1 = (float)value / 100.0f;
+    return h->fc_tc_ok ? pack_fc_images(h) : NMRGNN_OK;
+  }
+  if (std::strcmp(name, "fc_role_counters") == 0) {
+    if (value && !h->fc_dbg) {
+      CUDA_TRY(h, cudaMalloc(&h->fc_dbg, 1024 * 8 * sizeof(long long)));
+      h->owned.push_back((float*)h->fc_dbg);
+    }
+    if (value == 1) CUDA_TRY(h, cudaMemset(h->fc_dbg, 0, 1024 * 8 * sizeof(long long)));
+    if (value == 2 && h->fc_dbg) {
+      std::vector<long long> c(1024 * 8);
+      CUDA_TRY(h, cudaMemcpy(c.data(), h->fc_dbg, c.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double m[8] = {0};
+      int n = 0;
+      for (int b = 0; b < h->num_sms; ++b)
+        if (c[b * 8] > 0) {
+          ++n;
+          for (int i = 0; i < 8; ++i) m[i] += (double)c[b * 8 + i];
+        }
+      if (n)
+        printf("fc roles (mean cycles per CTA over %d CTAs): mma total %.0f | mma waits: operand chunks %.0f W %.0f | "
+               "epilogue busy %.0f | stager waits for X %.0f\n",
+               n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n);
+    }
+    if (value == 0) h->fc_dbg = nullptr;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_single_acc") == 0) {
