@@ -950,8 +950,9 @@ int pack_fc_images(nmrgnn_handle* h) {
       for (int hf = 0; hf < halves; ++hf)
         all.insert(all.end(), half_img[hf].begin() + (size_t)c * 16384, half_img[hf].begin() + (size_t)(c + 1) * 16384);
   }
-  // ---- layer-pipelined single-accumulator form (kernels_fc_pipe.cuh): per K = 16 step the instructions hi*hi, lo*hi,
-  // hi*lo all truncate the one accumulator, so the main product of step k (0..F/16-1) is truncated 3 (F/16 - k) times;
+  // ---- layer-pipelined single-accumulator form (kernels_fc_pipe.cuh): the 6 instructions of a 32-feature chunk -- main
+  // ks0, lo*hi ks0, main ks1, lo*hi ks1, hi*lo ks0, hi*lo ks1 -- all truncate the one accumulator, so a main product at
+  // position p of the 6 F/32 instructions is truncated 6 F/32 - p times;
   // W is pre-scaled by 2^s (s from max|w|: the unscaled lo image must stay in the normal fp16 range), 2^-s goes into
   // the epilogue's output scale.  Every layer's image takes 16 slots of 16 KB (the last one uses 8).
   {
@@ -967,7 +968,8 @@ int pack_fc_images(nmrgnn_handle* h) {
       while (sexp < 24 && wmax * std::ldexp(1.0f, sexp + 1) <= 32768.0f) ++sexp;
       h->fc_wsinv[i] = std::ldexp(1.0f, -sexp);
       pack_sw64_f16([&](int k, int n) { return W[(size_t)k * outw + n]; },
-                    [&](int k) { return cpos1 * (double)(n_instr1 - 3 * (k / 16)); }, F, outw, outw, img, std::ldexp(1.0, sexp),
+                    [&](int k) { return cpos1 * (double)(n_instr1 - (6 * (k / 32) + 2 * ((k % 32) / 16))); }, F, outw, outw, img,
+                    std::ldexp(1.0, sexp),
                     1.0);
       std::memcpy(all1.data() + (size_t)i * 16 * 16384, img.data(), img.size());
     }
@@ -1912,8 +1914,8 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
         }
       if (n)
         printf("fc roles (mean cycles per CTA over %d CTAs): mma total %.0f | mma waits: operand chunks %.0f W %.0f | "
-               "epilogue busy %.0f | stager waits for X %.0f\n",
-               n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n);
+               "epilogue busy %.0f | stager waits for X %.0f | W slots waited for %.0f, issue -> arrival %.0f cycles\n",
+               n, m[0] / n, m[1] / n, m[2] / n, m[3] / n, m[4] / n, m[6] / n, m[6] > 0 ? m[5] / m[6] : 0.0);
     }
     if (value == 0) h->fc_dbg = nullptr;
     return NMRGNN_OK;

@@ -48,11 +48,13 @@ struct FcPipeArgs {
 };
 
 constexpr int FPI_THREADS = 704;
-constexpr int FPI_RING = 4;
+constexpr int FPI_RING = 5;
 constexpr int FPI_CMAX = 16;
 constexpr size_t FPI_X_BYTES = 8 * 16384;
-constexpr size_t FPI_SMEM = 1024 + FPI_X_BYTES + FPI_RING * 16384 + MAX_DENSE * 256 * 4 + 128 * FPI_CMAX * 4 +
-                            2 * 4 * 128 * 4 + 2 * 4 * 128 * 4 + 3 * FPI_CMAX * 4 + 512;
+// (Wo and the per-class constants of the readout are read through L1 from global memory: that leaves room for a fifth
+//  W slot)
+constexpr size_t FPI_SMEM = 1024 + FPI_X_BYTES + FPI_RING * 16384 + MAX_DENSE * 256 * 4 + 2 * 4 * 128 * 4 +
+                            2 * 4 * 128 * 4 + 512;
 static_assert(FPI_SMEM <= 227 * 1024, "pipelined node-MLP kernel exceeds the 227 KB shared-memory limit");
 
 // exponent s with bound * 2^-s in [2^14, 2^15): fp16 operands stay finite with 2x margin, as large as possible
@@ -89,11 +91,9 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
   uint8_t* xs = smem;                                       // [8 chunks][hi 8192 | lo 8192]
   uint8_t* ring = xs + FPI_X_BYTES;                         // [RING][16384]
   float* bias_s = reinterpret_cast<float*>(ring + FPI_RING * SLOT);     // [n_layers][256]
-  float* wo_s = bias_s + MAX_DENSE * 256;                   // [128][C]
-  float* pm = wo_s + 128 * FPI_CMAX;                        // [2][4][128] partial row maxima of a layer's output
+  float* pm = bias_s + MAX_DENSE * 256;                     // [2][4][128] partial row maxima of a layer's output
   float* part = pm + 2 * 4 * 128;                           // [2][4][128] partial readout dot products
-  float* cls = part + 2 * 4 * 128;                          // bo | std | avg, FPI_CMAX each
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cls + 3 * FPI_CMAX);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 4 * 128);
   uint64_t* w_full = bars;                                  // [RING]
   uint64_t* w_empty = w_full + FPI_RING;                    // [RING]
   uint64_t* xs_full = w_empty + FPI_RING;                   // [8]  chunk staged (4 stager warps)
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
   uint64_t* x_free = d_full + 2;                            //      last layer's MMAs have read X
   uint64_t* d_free = x_free + 1;                            //      last layer's accumulators drained (odd layer counts)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_free + 1);
+  uint32_t* t_issue = tmem_slot + 2;                        // [RING] diagnostics: clock at which a slot's copy was issued
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nl = p.n_layers, C = p.C;
@@ -121,12 +122,6 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
     tc::mbar_fence_init();
   }
   for (int i = tid; i < nl * 256; i += FPI_THREADS) bias_s[i] = p.bias[i];
-  for (int i = tid; i < 128 * C; i += FPI_THREADS) wo_s[i] = p.Wo[i];
-  if (tid < C) {
-    cls[tid] = p.bo[tid];
-    cls[FPI_CMAX + tid] = p.peak_std[tid];
-    cls[2 * FPI_CMAX + tid] = p.peak_avg[tid];
-  }
   if (warp == 1) {
     tc::tmem_alloc<512>(tmem_slot);
   }
@@ -154,6 +149,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
             const uint32_t slot = it % FPI_RING, ph = (it / FPI_RING) & 1;
             tc::mbar_wait(&w_empty[slot], ph ^ 1);
             tc::mbar_expect_tx(&w_full[slot], SLOT);
+            if (p.dbg) *reinterpret_cast<volatile uint32_t*>(&t_issue[slot]) = (uint32_t)clock64();
             tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * SLOT, SLOT, &w_full[slot]);
           }
         }
@@ -163,7 +159,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
     if (lane == 0) {
       const uint32_t idesc256 = tc::make_idesc_f16(128, 256), idesc128 = tc::make_idesc_f16(128, 128);
       uint32_t it = 0, t = 0, ne = 0;
-      long long w_x = 0, w_w = 0, c0 = 0;
+      long long w_x = 0, w_w = 0, c0 = 0, lat_sum = 0, lat_n = 0;
       const long long k0 = clock64();
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
         if ((nl & 1) && t > 0) {          // odd layer count: layer 0 shares its set with the previous tile's last layer
@@ -185,19 +181,34 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
               const uint32_t s_hi = it % FPI_RING, s_lo = (it + 1) % FPI_RING;
               if (p.dbg) c0 = clock64();
               tc::mbar_wait(&w_full[s_hi], (it / FPI_RING) & 1);
-              tc::mbar_wait(&w_full[s_lo], ((it + 1) / FPI_RING) & 1);
-              if (p.dbg) w_w += clock64() - c0;
+              if (p.dbg) {
+                const long long now = clock64();
+                w_w += now - c0;
+                if (now - c0 > 100) {
+                  lat_sum += (uint32_t)((uint32_t)now - *reinterpret_cast<volatile uint32_t*>(&t_issue[s_hi]));
+                  ++lat_n;
+                }
+              }
               tc::tc_fence_after();
               const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + s_hi * SLOT));
               const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(ring + s_lo * SLOT));
+              // instruction order of a chunk: hi*hi, lo*hi (ks 0), hi*hi, lo*hi (ks 1), then hi*lo (ks 0, 1) from the next slot
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);
                 tc::umma_f16(d, ah + adv, bh + adv, idesc256, (c | ks) != 0);
                 tc::umma_f16(d, al + adv, bh + adv, idesc256, 1);
-                tc::umma_f16(d, ah + adv, bl + adv, idesc256, 1);
               }
               tc::umma_commit(&w_empty[s_hi]);
+              if (p.dbg) c0 = clock64();
+              tc::mbar_wait(&w_full[s_lo], ((it + 1) / FPI_RING) & 1);
+              if (p.dbg) w_w += clock64() - c0;
+              tc::tc_fence_after();
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                tc::umma_f16(d, ah + adv, bl + adv, idesc256, 1);
+              }
               tc::umma_commit(&w_empty[s_lo]);
               it += 2;
             } else {
@@ -213,6 +224,10 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
                 const uint64_t adv = (uint64_t)(ks * 2);
                 tc::umma_f16(d, ah + adv, bh + adv, idesc128, (c | ks) != 0);
                 tc::umma_f16(d, al + adv, bh + adv, idesc128, 1);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
                 tc::umma_f16(d, ah + adv, bl + adv, idesc128, 1);
               }
               tc::umma_commit(&w_empty[slot]);
@@ -229,6 +244,8 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
         o[0] = clock64() - k0;   // MMA thread: total
         o[1] = w_x;              //   waiting for operand chunks (stagers / epilogue)
         o[2] = w_w;              //   waiting for W
+        o[5] = lat_sum;          //   issue -> arrival of the W hi slots it had to wait for (sum, count)
+        o[6] = lat_n;
       }
     }
   } else if (warp < 18) {
@@ -357,11 +374,11 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
         while (mk) {
           const int c = __ffs(mk) - 1;
           mk &= mk - 1;
-          const float* w = wo_s + (32 * j) * C + c;
+          const float* w = p.Wo + (32 * j) * C + c;
           float dot = 0.0f;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) dot = fmaf(z[k], w[k * C], dot);
-          partial = onehot ? dot : fmaf(dot, __ldg(ar + c) * cls[FPI_CMAX + c], partial);
+          for (int k = 0; k < 32; ++k) dot = fmaf(z[k], __ldg(w + k * C), dot);
+          partial = onehot ? dot : fmaf(dot, __ldg(ar + c) * __ldg(p.peak_std + c), partial);
         }
         float* pt = part + (t & 1) * 512;
         pt[j * 128 + row] = partial;
@@ -372,7 +389,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
           if (onehot) {
             const int c = __ffs(cmask) - 1;
             const float a = __ldg(ar + c);
-            peak = (dsum + cls[c]) * a * cls[FPI_CMAX + c] + a * cls[2 * FPI_CMAX + c];
+            peak = (dsum + __ldg(p.bo + c)) * a * __ldg(p.peak_std + c) + a * __ldg(p.peak_avg + c);
           } else {
             peak = dsum;
             mk = cmask;
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
               const int c = __ffs(mk) - 1;
               mk &= mk - 1;
               const float a = __ldg(ar + c);
-              peak += cls[c] * a * cls[FPI_CMAX + c] + a * cls[2 * FPI_CMAX + c];
+              peak += __ldg(p.bo + c) * a * __ldg(p.peak_std + c) + a * __ldg(p.peak_avg + c);
             }
           }
           p.peaks[a0 + row] = peak;

@@ -504,6 +504,59 @@ def test_single_accumulator_kernel_within_tolerance(model, config2_batch):
     assert np.array_equal(model((atoms, nlist, edges, inv)), y0)
 
 
+@pytest.mark.gpu
+def test_pipelined_node_mlp_kernel(model, config2_batch):
+    """The layer-pipelined node-MLP kernel (option fc_pipe, the default; one accumulator per layer, layer l + 1 under the
+    epilogue of layer l, readout from registers) and the round-1 kernel (fc_pipe = 0): both within the tolerance on every
+    atom of the full bench batch against the fp64 golden peaks (measured max 0.63 / 0.53), graphs independent of their
+    batch and position in a tile, the block entry point (fc_nodes) against the traced graph, multi-hot atom rows."""
+    from nmrgnn_b200.workloads import take_graphs
+    ref64, _ = _full_fixture("full_config2", config2_batch)
+    atoms, nlist, edges, inv, offs = config2_batch
+    h = model.handle
+    ys = {}
+    try:
+        for pipe in (1, 0):
+            h.set_option("fc_pipe", pipe)
+            ys[pipe] = model((atoms, nlist, edges, inv))
+            e = _err(ys[pipe], ref64)
+            print(f"fc_pipe={pipe}: max", round(float(e.max()), 3), "p99.99", round(float(np.quantile(e, 0.9999)), 3))
+            assert e.max() <= 1.0 and np.quantile(e, 0.9999) <= 0.5
+            assert np.array_equal(ys[pipe] == 0, ref64 == 0)
+        assert not np.array_equal(ys[0], ys[1])
+        h.set_option("fc_pipe", 1)
+        sub = take_graphs(config2_batch, np.array([11, 40]))          # other tile positions, partial last tile
+        a, b = int(offs[11]), int(offs[12])
+        assert np.array_equal(model(sub[:4])[: b - a], ys[1][a:b])
+        # block entry point: Z of the last dense layer and the peaks from given node features (row maxima computed here)
+        h.set_option("tc_min_atoms", 0)
+        g = load_golden("prot300")
+        n = g["atoms"].shape[0]
+        for pipe in (1, 0):
+            h.set_option("fc_pipe", pipe)
+            peaks, fcn = np.zeros(n, np.float32), np.zeros((n, 128), np.float32)
+            h.fc_readout(np.ascontiguousarray(g["mp_nodes_3"]), np.ascontiguousarray(g["atoms"]), n, peaks, fcn, 0)
+            assert np.abs(fcn - g["fc_nodes"]).max() <= 2e-6 * np.abs(g["fc_nodes"]).max(), pipe
+            assert tol_ratio(peaks, g["peaks_f64"]) <= 0.1, pipe
+        # multi-hot / scaled atom rows: the readout is linear in the atom row for fixed node features
+        h.set_option("fc_pipe", 1)
+        rng = np.random.default_rng(5)
+        nodes = np.ascontiguousarray(g["mp_nodes_3"])
+        a1 = np.zeros((n, 10), np.float32)
+        a2 = np.zeros((n, 10), np.float32)
+        a1[np.arange(n), rng.integers(2, 5, n)] = 1.0
+        a2[np.arange(n), rng.integers(5, 8, n)] = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        out = []
+        for a in (a1, a2, a1 + a2):
+            pk = np.zeros(n, np.float32)
+            h.fc_readout(nodes, a, n, pk, None, 0)
+            out.append(pk.astype(np.float64))
+        assert np.allclose(out[2], out[0] + out[1], rtol=2e-6, atol=2e-5)
+    finally:
+        h.set_option("fc_pipe", 1)
+        h.set_option("tc_min_atoms", 1024)
+
+
 def test_column_split_pair_kernel_is_bit_identical(model, config2_batch):
     """Option mp_nsplit: the MP layers on column-split CTA pairs (cluster of 2, operand halves shipped through
     distributed shared memory, double-buffered accumulators) give the same bits as the one-CTA kernel -- on the full
@@ -697,9 +750,12 @@ def test_second_weight_set_on_tensor_cores_against_oracle():
     from nmrgnn_b200.params import baseline_standards
     from oracle import forward as orc
     std, avg = baseline_standards(10)
-    for seed, mp_act, fc_act in ((11, "softplus", "softplus"), (12, "tanh", "softplus"), (13, "relu", "relu")):
+    # (odd node-MLP layer counts: layer 0 of the pipelined kernel shares its accumulator set with the previous tile's
+    #  last layer and waits for its drain)
+    for seed, mp_act, fc_act, n_fc in ((11, "softplus", "softplus", 4), (12, "tanh", "softplus", 4), (13, "relu", "relu", 4),
+                                       (14, "softplus", "softplus", 3), (15, "softplus", "tanh", 5)):
         m = nmrgnn_b200.build_GNNModel(dict(atom_feature_size=256, edge_feature_size=3, edge_hidden_size=128, mp_layers=4,
-                                            fc_layers=4, edge_fc_layers=4, mp_activation=mp_act, fc_activation=fc_act),
+                                            fc_layers=n_fc, edge_fc_layers=4, mp_activation=mp_act, fc_activation=fc_act),
                                        num_elem=10, seed=seed, peak_std=std, peak_avg=avg)
         try:
             m.handle.set_option("tc_min_atoms", 0)
@@ -712,7 +768,7 @@ def test_second_weight_set_on_tensor_cores_against_oracle():
                 m.handle.set_option("force_ffma", 1)
                 r_ffma = tol_ratio(m((atoms, nlist, edges, inv)), ref)
                 m.handle.set_option("force_ffma", 0)
-                print(f"seed {seed} {mp_act}/{fc_act} K={k}: tensor cores {r:.3f}, exact-FP32 kernels {r_ffma:.3f} "
+                print(f"seed {seed} {mp_act}/{fc_act}/{n_fc} fc layers K={k}: tensor cores {r:.3f}, exact-FP32 kernels {r_ffma:.3f} "
                       f"(path {m.handle.compute_path}, compensation {m.handle.tc_compensation()})")
                 assert r <= 1.0 and r_ffma <= 1.0
         finally:
