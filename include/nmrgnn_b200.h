@@ -204,6 +204,8 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *                  (kernels_fc_pipe.cuh, default 1: one accumulator per layer, two sets in tensor memory, layer l + 1
  *                  accumulates K-chunk by K-chunk under the epilogue of layer l, the next tile is staged by its own
  *                  warps, the readout is formed from registers);
+ *   "fc_pair" = 1: the pipelined node-MLP kernel on CTA pairs (cta_group::2: two tiles per M = 256 instruction, each
+ *                  CTA stages half of every W tile); same arithmetic per tile, bit-identical results;
  *   "fc_pos_comp1_x100" = v: slope of the pipelined kernel's position-dependent compensation (48-instruction chains,
  *                  default 50);
  *   "fc_role_counters" = 1 / 2 / 0: diagnostics -- arm / print / disarm per-CTA cycle counters of the pipelined node-MLP

@@ -109,6 +109,8 @@ struct nmrgnn_handle {
   float fc_rz = 1.0f;
   // layer-pipelined single-accumulator form of the node MLP (kernels_fc_pipe.cuh): its own images, scales and bounds
   bool fc_pipe = true;                  // option "fc_pipe"
+  bool fc_pair = false;                 // option "fc_pair": the pipelined kernel on CTA pairs (cta_group::2)
+  const uint8_t* fc_img1p = nullptr;    // its images: per layer [2 ranks][8 chunks][hi 8192 | lo 8192] (last: [hi 4096 | lo 4096])
   const uint8_t* fc_img1 = nullptr;     // per layer [8 chunks][hi 16384 | lo 16384] (last: [hi 8192 | lo 8192]), W x 2^s, lo unscaled
   float fc_wsinv[MAX_DENSE];            // per layer 2^-s
   float fc_g1[MAX_DENSE], fc_o1[MAX_DENSE];   // one-layer growth bound: max|x_{l+1}| <= g max|x_l| + o
@@ -787,7 +789,13 @@ int launch_fc(nmrgnn_handle* h, cudaStream_t s, const float* nodes, const float*
     t.peak_avg = h->peak_avg;
     t.dbg = h->fc_dbg;
     const int64_t tiles = (n + 127) / 128;
-    ACT_DISPATCH(t.act, fc_readout_pipe_kernel, grid_for(h, tiles, 1), FPI_THREADS, FPI_SMEM, s, t);
+    if (h->fc_pair && h->fc_img1p) {
+      t.Wimg = h->fc_img1p;
+      const int64_t pairs = std::min<int64_t>((tiles + 1) / 2, h->num_sms / 2);
+      ACT_DISPATCH(t.act, fc_readout_pipe_pair_kernel, (unsigned)(2 * pairs), FPI_THREADS, FPI_SMEM_PAIR, s, t);
+    } else {
+      ACT_DISPATCH(t.act, fc_readout_pipe_kernel, grid_for(h, tiles, 1), FPI_THREADS, FPI_SMEM, s, t);
+    }
     h->launches++;
     return NMRGNN_OK;
   }
@@ -958,7 +966,7 @@ int pack_fc_images(nmrgnn_handle* h) {
   {
     const double cpos1 = h->compensate ? (double)h->fc_pos_c1 / 16777216.0 : 0.0;
     const int n_instr1 = 3 * (F / 16);
-    std::vector<uint8_t> all1((size_t)n_fc * 16 * 16384, 0), img;
+    std::vector<uint8_t> all1((size_t)n_fc * 16 * 16384, 0), all1p((size_t)n_fc * 16 * 16384, 0), img;
     for (int i = 0; i < n_fc; ++i) {
       const bool last = (i == n_fc - 1);
       const int outw = last ? F / 2 : F;
@@ -972,6 +980,20 @@ int pack_fc_images(nmrgnn_handle* h) {
                     std::ldexp(1.0, sexp),
                     1.0);
       std::memcpy(all1.data() + (size_t)i * 16 * 16384, img.data(), img.size());
+      // CTA-pair form: CTA r of a pair stages N rows [r outw/2, (r + 1) outw/2) of every tile
+      for (int r = 0; r < 2; ++r) {
+        const int half = outw / 2;
+        pack_sw64_f16([&](int k, int n) { return W[(size_t)k * outw + r * half + n]; },
+                      [&](int k) { return cpos1 * (double)(n_instr1 - (6 * (k / 32) + 2 * ((k % 32) / 16))); }, F, half, half, img,
+                      std::ldexp(1.0, sexp), 1.0);
+        std::memcpy(all1p.data() + (size_t)i * 16 * 16384 + (size_t)r * img.size(), img.data(), img.size());
+      }
+    }
+    if (!h->fc_img1p) {
+      if (int rc = upload_bytes(h, all1p.data(), all1p.size(), &h->fc_img1p)) return rc;
+    } else {
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpy(const_cast<uint8_t*>(h->fc_img1p), all1p.data(), all1p.size(), cudaMemcpyHostToDevice));
     }
     if (!h->fc_img1) {
       if (int rc = upload_bytes(h, all1.data(), all1.size(), &h->fc_img1)) return rc;
@@ -1397,6 +1419,7 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     h->fc_rz = 1.0f;
     ACT_SET_SMEM(fc_readout_tc_kernel, FTC_SMEM);
     ACT_SET_SMEM(fc_readout_pipe_kernel, FPI_SMEM);
+    ACT_SET_SMEM(fc_readout_pipe_pair_kernel, FPI_SMEM_PAIR);
   }
   update_path(h);
 #undef TRY_RC
@@ -1889,6 +1912,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
   }
   if (std::strcmp(name, "fc_pipe") == 0) {
     h->fc_pipe = value != 0;
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "fc_pair") == 0) {
+    h->fc_pair = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "fc_pos_comp1_x100") == 0) {  // slope of the pipelined node MLP's position-dependent compensation

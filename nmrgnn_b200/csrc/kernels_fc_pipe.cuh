@@ -48,14 +48,21 @@ struct FcPipeArgs {
 };
 
 constexpr int FPI_THREADS = 704;
-constexpr int FPI_RING = 5;
+// W ring.  One CTA: 2 slots of 32 KB = the hi and lo tiles (256 N rows each) of one 32-feature chunk, ONE bulk copy each
+// (a bulk copy costs its latency whatever its size, and under load that latency is thousands of cycles).  CTA pair:
+// every CTA stages only its 128 N rows of both tiles, 16 KB per chunk, so the same bytes hold 5 chunks.
+constexpr int FPI_RING = 2;
+constexpr int FPI_SLOT = 32768;
+constexpr int FPI_RING_PAIR = 5;
+constexpr int FPI_SLOT_PAIR = 16384;
 constexpr int FPI_CMAX = 16;
 constexpr size_t FPI_X_BYTES = 8 * 16384;
 // (Wo and the per-class constants of the readout are read through L1 from global memory: that leaves room for a fifth
 //  W slot)
-constexpr size_t FPI_SMEM = 1024 + FPI_X_BYTES + FPI_RING * 16384 + MAX_DENSE * 256 * 4 + 2 * 4 * 128 * 4 +
+constexpr size_t FPI_SMEM = 1024 + FPI_X_BYTES + FPI_RING * FPI_SLOT + MAX_DENSE * 256 * 4 + 2 * 4 * 128 * 4 +
                             2 * 4 * 128 * 4 + 512;
-static_assert(FPI_SMEM <= 227 * 1024, "pipelined node-MLP kernel exceeds the 227 KB shared-memory limit");
+constexpr size_t FPI_SMEM_PAIR = FPI_SMEM + (FPI_RING_PAIR * FPI_SLOT_PAIR - FPI_RING * FPI_SLOT);
+static_assert(FPI_SMEM_PAIR <= 227 * 1024 && FPI_SMEM <= 227 * 1024, "pipelined node-MLP kernel exceeds the 227 KB shared-memory limit");
 
 // exponent s with bound * 2^-s in [2^14, 2^15): fp16 operands stay finite with 2x margin, as large as possible
 __device__ __forceinline__ int fpi_scale_exp(float bound) {
@@ -83,20 +90,22 @@ __device__ __forceinline__ void fpi_split8_plain(const float (&x)[8], uint4& hi,
   tc::split2_f16_plain(x[6], x[7], hi.w, lo.w);
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const FcPipeArgs p) {
-  constexpr int SLOT = 16384;
+template <int ACT, bool PAIR>
+__device__ __forceinline__ void fc_readout_pipe_body(const FcPipeArgs& p) {
+  constexpr int SLOT = PAIR ? FPI_SLOT_PAIR : FPI_SLOT;
+  constexpr int RING = PAIR ? FPI_RING_PAIR : FPI_RING;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* xs = smem;                                       // [8 chunks][hi 8192 | lo 8192]
   uint8_t* ring = xs + FPI_X_BYTES;                         // [RING][16384]
-  float* bias_s = reinterpret_cast<float*>(ring + FPI_RING * SLOT);     // [n_layers][256]
+  float* bias_s = reinterpret_cast<float*>(ring + RING * SLOT);         // [n_layers][256]
   float* pm = bias_s + MAX_DENSE * 256;                     // [2][4][128] partial row maxima of a layer's output
   float* part = pm + 2 * 4 * 128;                           // [2][4][128] partial readout dot products
   uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 4 * 128);
   uint64_t* w_full = bars;                                  // [RING]
-  uint64_t* w_empty = w_full + FPI_RING;                    // [RING]
-  uint64_t* xs_full = w_empty + FPI_RING;                   // [8]  chunk staged (4 stager warps)
+  uint64_t* w_empty = w_full + RING;                        // [RING]
+  uint64_t* w_peer = w_empty + RING;                        // [RING] (pair, leader: the peer's half of the slot has landed)
+  uint64_t* xs_full = w_peer + RING;                        // [8]  chunk staged (4 stager warps; pair: of both CTAs, on the leader)
   uint64_t* xe_full = xs_full + 8;                          // [8]  chunk rewritten by an epilogue (16 warps)
   uint64_t* d_full = xe_full + 8;                           // [2]  accumulator set complete
   uint64_t* x_free = d_full + 2;                            //      last layer's MMAs have read X
@@ -106,64 +115,107 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nl = p.n_layers, C = p.C;
+  const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
   if (tid == 0) {
-    for (int i = 0; i < FPI_RING; ++i) {
+    for (int i = 0; i < RING; ++i) {
       tc::mbar_init(&w_full[i], 1);
       tc::mbar_init(&w_empty[i], 1);
+      tc::mbar_init(&w_peer[i], 1);
     }
-    for (int i = 0; i < 8; ++i) {
-      tc::mbar_init(&xs_full[i], 4);
-      tc::mbar_init(&xe_full[i], 16);
+    for (int i = 0; i < 8; ++i) {          // pair: the warps of both CTAs arrive on the leader's barriers
+      tc::mbar_init(&xs_full[i], PAIR ? 8 : 4);
+      tc::mbar_init(&xe_full[i], PAIR ? 32 : 16);
     }
     tc::mbar_init(&d_full[0], 1);
     tc::mbar_init(&d_full[1], 1);
     tc::mbar_init(x_free, 1);
-    tc::mbar_init(d_free, 16);
+    tc::mbar_init(d_free, PAIR ? 32 : 16);
     tc::mbar_fence_init();
   }
   for (int i = tid; i < nl * 256; i += FPI_THREADS) bias_s[i] = p.bias[i];
   if (warp == 1) {
-    tc::tmem_alloc<512>(tmem_slot);
+    if (PAIR) tc::tmem_alloc_pair<512>(tmem_slot);
+    else tc::tmem_alloc<512>(tmem_slot);
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();            // both CTAs' barriers exist before any remote arrive / multicast commit
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int64_t n_tiles = (p.n_atoms + 127) / 128;
-  const int64_t tile_first = (int64_t)blockIdx.x;
+  // tile walk: a single CTA takes tiles blockIdx.x, + gridDim.x, ...; a pair takes tile pairs and CTA r the r-th tile of
+  // each pair (a trailing odd tile leaves the peer with an empty tile: it still runs the whole protocol)
+  const int64_t tile_first = PAIR ? (int64_t)(blockIdx.x >> 1) * 2 + rank : (int64_t)blockIdx.x;
   const int64_t tile_step = (int64_t)gridDim.x;
-  const int64_t tile_end = n_tiles;
+  const int64_t tile_end = PAIR ? ((n_tiles + 1) / 2) * 2 : n_tiles;
+  // the leader's hand-off barriers as seen from either CTA of the pair
+  const uint32_t xs_full_a = PAIR ? tc::map_to_cta(tc::smem_u32(xs_full), 0) : tc::smem_u32(xs_full);
+  const uint32_t xe_full_a = PAIR ? tc::map_to_cta(tc::smem_u32(xe_full), 0) : tc::smem_u32(xe_full);
+  const uint32_t d_free_a = PAIR ? tc::map_to_cta(tc::smem_u32(d_free), 0) : tc::smem_u32(d_free);
+  auto arrive = [&](uint32_t addr) {       // one arrival on a hand-off barrier (pair: release at cluster scope)
+    if (PAIR) tc::mbar_arrive_cluster(addr);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+  };
   // accumulator set of layer l: the last layer always takes set 1, so that with an even layer count layer 0 of the
   // next tile (set 0) never meets the set the last epilogue is still reading
   const int set0 = (nl & 1) ? 1 : 0;                        // set of layer 0; layer l: (set0 + l) & 1
 
   if (warp == 0) {
     // ===================== W loader =====================
+    // one CTA: chunk = [hi 16384 | lo 16384] (last layer: two chunks of [hi 8192 | lo 8192]) per 32 KB copy;
+    // pair: this CTA's 128 (64) N rows: chunk = [hi 8192 | lo 8192] (last layer: two chunks of [hi 4096 | lo 4096]) per 16 KB copy
     if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
         for (int l = 0; l < nl; ++l) {
-          const int n_slots = (l == nl - 1) ? 8 : 16;
-          const uint8_t* src = p.Wimg + (size_t)l * 16 * SLOT;
-          for (int q = 0; q < n_slots; ++q, ++it) {
-            const uint32_t slot = it % FPI_RING, ph = (it / FPI_RING) & 1;
-            tc::mbar_wait(&w_empty[slot], ph ^ 1);
+          const int n_ops = (l == nl - 1) ? 4 : 8;
+          const uint8_t* src = p.Wimg + (size_t)l * 262144 + (PAIR ? (size_t)rank * (l == nl - 1 ? 65536 : 131072) : 0);
+          for (int q = 0; q < n_ops; ++q, ++it) {
+            const uint32_t slot = it % RING, ph = (it / RING) & 1;
+            tc::mbar_wait_susp(&w_empty[slot], ph ^ 1);
             tc::mbar_expect_tx(&w_full[slot], SLOT);
             if (p.dbg) *reinterpret_cast<volatile uint32_t*>(&t_issue[slot]) = (uint32_t)clock64();
             tc::bulk_g2s(ring + slot * SLOT, src + (size_t)q * SLOT, SLOT, &w_full[slot]);
           }
         }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && PAIR && rank != 0) {
+    // ===================== peer CTA: relay "my half of the slot has landed" to the leader =====================
     if (lane == 0) {
-      const uint32_t idesc256 = tc::make_idesc_f16(128, 256), idesc128 = tc::make_idesc_f16(128, 128);
+      const uint32_t w_peer_ldr = tc::map_to_cta(tc::smem_u32(w_peer), 0);
+      uint32_t it = 0;
+      for (int64_t tile = tile_first; tile < tile_end; tile += tile_step)
+        for (int l = 0; l < nl; ++l) {
+          const int n_ops = (l == nl - 1) ? 4 : 8;
+          for (int q = 0; q < n_ops; ++q, ++it) {
+            const uint32_t slot = it % RING;
+            tc::mbar_wait_susp(&w_full[slot], (it / RING) & 1);
+            tc::mbar_arrive_cluster(w_peer_ldr + slot * 8u);
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair: the leader CTA only) =====================
+    if (lane == 0) {
+      const uint32_t idesc256 = tc::make_idesc_f16(PAIR ? 256 : 128, 256), idesc128 = tc::make_idesc_f16(PAIR ? 256 : 128, 128);
+      auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+        if (PAIR) tc::umma_f16_pair(d, a, b, idesc, acc);
+        else tc::umma_f16(d, a, b, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {       // pair: the arrival goes to the same barrier of both CTAs
+        if (PAIR) tc::umma_commit_pair(bar, 3);
+        else tc::umma_commit(bar);
+      };
+      auto wait = [&](uint64_t* bar, uint32_t parity) {   // barriers with arrivals from the peer CTA
+        if (PAIR) tc::mbar_wait_cluster(bar, parity);
+        else tc::mbar_wait(bar, parity);
+      };
       uint32_t it = 0, t = 0, ne = 0;
       long long w_x = 0, w_w = 0, c0 = 0, lat_sum = 0, lat_n = 0;
       const long long k0 = clock64();
       for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
         if ((nl & 1) && t > 0) {          // odd layer count: layer 0 shares its set with the previous tile's last layer
-          tc::mbar_wait(d_free, (t - 1) & 1);
+          wait(d_free, (t - 1) & 1);
           tc::tc_fence_after();
         }
         for (int l = 0; l < nl; ++l) {
@@ -171,71 +223,67 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
           const uint32_t d = tmem_base + (uint32_t)((set0 + l) & 1) * 256u;
           for (int c = 0; c < 8; ++c) {
             if (p.dbg) c0 = clock64();
-            if (l == 0) tc::mbar_wait(&xs_full[c], t & 1);
-            else tc::mbar_wait(&xe_full[c], ne & 1);
+            if (l == 0) wait(&xs_full[c], t & 1);
+            else wait(&xe_full[c], ne & 1);
             if (p.dbg) w_x += clock64() - c0;
             tc::tc_fence_after();
             const uint64_t ah = tc::make_desc_sw64(tc::smem_u32(xs + c * 16384));
             const uint64_t al = tc::make_desc_sw64(tc::smem_u32(xs + c * 16384 + 8192));
-            if (!last) {
-              const uint32_t s_hi = it % FPI_RING, s_lo = (it + 1) % FPI_RING;
+            const uint32_t slot = it % RING;
+            if (!last || (c & 1) == 0) {
               if (p.dbg) c0 = clock64();
-              tc::mbar_wait(&w_full[s_hi], (it / FPI_RING) & 1);
+              tc::mbar_wait(&w_full[slot], (it / RING) & 1);
+              if (PAIR) tc::mbar_wait_cluster(&w_peer[slot], (it / RING) & 1);
               if (p.dbg) {
                 const long long now = clock64();
                 w_w += now - c0;
                 if (now - c0 > 100) {
-                  lat_sum += (uint32_t)((uint32_t)now - *reinterpret_cast<volatile uint32_t*>(&t_issue[s_hi]));
+                  lat_sum += (uint32_t)((uint32_t)now - *reinterpret_cast<volatile uint32_t*>(&t_issue[slot]));
                   ++lat_n;
                 }
               }
               tc::tc_fence_after();
-              const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + s_hi * SLOT));
-              const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(ring + s_lo * SLOT));
-              // instruction order of a chunk: hi*hi, lo*hi (ks 0), hi*hi, lo*hi (ks 1), then hi*lo (ks 0, 1) from the next slot
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                tc::umma_f16(d, ah + adv, bh + adv, idesc256, (c | ks) != 0);
-                tc::umma_f16(d, al + adv, bh + adv, idesc256, 1);
-              }
-              tc::umma_commit(&w_empty[s_hi]);
-              if (p.dbg) c0 = clock64();
-              tc::mbar_wait(&w_full[s_lo], ((it + 1) / FPI_RING) & 1);
-              if (p.dbg) w_w += clock64() - c0;
-              tc::tc_fence_after();
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t adv = (uint64_t)(ks * 2);
-                tc::umma_f16(d, ah + adv, bl + adv, idesc256, 1);
-              }
-              tc::umma_commit(&w_empty[s_lo]);
-              it += 2;
-            } else {
-              const uint32_t slot = it % FPI_RING;
-              if (p.dbg) c0 = clock64();
-              tc::mbar_wait(&w_full[slot], (it / FPI_RING) & 1);
-              if (p.dbg) w_w += clock64() - c0;
-              tc::tc_fence_after();
+            }
+            // instruction order of a chunk: hi*hi, lo*hi (ks 0), hi*hi, lo*hi (ks 1), hi*lo (ks 0, 1)
+            if (!last) {
               const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT));
-              const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT + 8192));
+              const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(ring + slot * SLOT + SLOT / 2));
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);
-                tc::umma_f16(d, ah + adv, bh + adv, idesc128, (c | ks) != 0);
-                tc::umma_f16(d, al + adv, bh + adv, idesc128, 1);
+                mma(d, ah + adv, bh + adv, idesc256, (c | ks) != 0);
+                mma(d, al + adv, bh + adv, idesc256, 1);
               }
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
                 const uint64_t adv = (uint64_t)(ks * 2);
-                tc::umma_f16(d, ah + adv, bl + adv, idesc128, 1);
+                mma(d, ah + adv, bl + adv, idesc256, 1);
               }
-              tc::umma_commit(&w_empty[slot]);
+              commit(&w_empty[slot]);
               it += 1;
+            } else {
+              const uint8_t* wb = ring + slot * SLOT + (c & 1) * (SLOT / 2);
+              const uint64_t bh = tc::make_desc_sw64(tc::smem_u32(wb));
+              const uint64_t bl = tc::make_desc_sw64(tc::smem_u32(wb + SLOT / 4));
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                mma(d, ah + adv, bh + adv, idesc128, (c | ks) != 0);
+                mma(d, al + adv, bh + adv, idesc128, 1);
+              }
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t adv = (uint64_t)(ks * 2);
+                mma(d, ah + adv, bl + adv, idesc128, 1);
+              }
+              if (c & 1) {
+                commit(&w_empty[slot]);
+                it += 1;
+              }
             }
           }
-          tc::umma_commit(&d_full[(set0 + l) & 1]);
-          if (last) tc::umma_commit(x_free);
+          commit(&d_full[(set0 + l) & 1]);
+          if (last) commit(x_free);
           if (l > 0) ++ne;
         }
       }
@@ -259,7 +307,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
     long long e_busy = 0;
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
-      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));   // 0: the pair's trailing empty tile
       // this row's input maximum and element classes (loads in flight while layer 0 accumulates)
       float m_in = 0.0f;
       uint32_t cmask = 0;
@@ -275,7 +323,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
         const uint32_t t_set = t_lane + (uint32_t)set * 256u + (uint32_t)(8 * j);
         const uint32_t bl_a = tc::smem_u32(bias_s + l * 256 + 8 * j);
         float mx = 0.0f;
-        tc::mbar_wait(&d_full[set], (dphase >> set) & 1);
+        tc::mbar_wait_susp(&d_full[set], (dphase >> set) & 1);
         dphase ^= 1u << set;
         const long long e0 = p.dbg ? clock64() : 0;
         tc::tc_fence_after();
@@ -318,7 +366,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
           tc::fence_proxy_async();
           tc::tc_fence_before();
           __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&xe_full[s]);
+          if (lane == 0) arrive(xe_full_a + (uint32_t)s * 8u);
         };
 #pragma unroll 1
         for (int s = 0; s < 8; ++s) step(s);
@@ -332,7 +380,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
         const float s_out = p.corr * tc::pow2f_exact(e_in) * p.wsinv[l];
         const uint32_t t_set = t_lane + (uint32_t)set * 256u + (uint32_t)(32 * j);
         const uint32_t bl_a = tc::smem_u32(bias_s + l * 256 + 32 * j);
-        tc::mbar_wait(&d_full[set], (dphase >> set) & 1);
+        tc::mbar_wait_susp(&d_full[set], (dphase >> set) & 1);
         dphase ^= 1u << set;
         const long long e0 = p.dbg ? clock64() : 0;
         tc::tc_fence_after();
@@ -350,7 +398,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
         }
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(d_free);
+        if (lane == 0) arrive(d_free_a);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 b4 = tc::lds128(bl_a + (uint32_t)i * 4u);
@@ -417,7 +465,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
     long long s_wait = 0;
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       const int64_t a0 = tile * 128;
-      const int rows = (int)min((int64_t)128, p.n_atoms - a0);
+      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
       float sc[4];
       const int r0 = 32 * sw + r8;            // this lane's rows: r0 + 8 g
 #pragma unroll
@@ -445,7 +493,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
       load(0, buf[0]);
       if (t > 0) {                         // the previous tile's last layer has read X
         const long long c0 = p.dbg ? clock64() : 0;
-        tc::mbar_wait(x_free, (t - 1) & 1);
+        tc::mbar_wait_susp(x_free, (t - 1) & 1);
         if (p.dbg) s_wait += clock64() - c0;
       }
 #pragma unroll
@@ -464,7 +512,7 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
         }
         tc::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&xs_full[c]);
+        if (lane == 0) arrive(xs_full_a + (uint32_t)c * 8u);
       }
       // pull the CTA's next tile into L2 (pure hint)
       const int64_t nt = tile + tile_step;
@@ -478,9 +526,25 @@ __global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const F
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (PAIR) tc::cluster_sync();            // the leader's MMAs read the peer's shared memory until the very end
   if (warp == 1) {
-    tc::tmem_dealloc<512>(tmem_base);
+    if (PAIR) tc::tmem_dealloc_pair<512>(tmem_base);
+    else tc::tmem_dealloc<512>(tmem_base);
   }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_kernel(const FcPipeArgs p) {
+  fc_readout_pipe_body<ACT, false>(p);
+}
+
+// CTA-pair form (cta_group::2, option "fc_pair"): the two CTAs of a cluster work on two neighbouring tiles with ONE
+// M = 256 instruction stream issued by the leader; each CTA stages only its 128 N rows of every W tile.  Per SM that is
+// a third less tensor-core operand traffic and half the W traffic through the shared-memory pipe -- the pipe that
+// bounds the one-CTA kernel -- and one instruction stream for two tiles.
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FPI_THREADS, 1) fc_readout_pipe_pair_kernel(const FcPipeArgs p) {
+  fc_readout_pipe_body<ACT, true>(p);
 }
 
 }  // namespace nmr

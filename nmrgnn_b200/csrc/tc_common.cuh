@@ -93,6 +93,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) { mbar_wait_t<4000>(bar, parity); }
+// Hardware-suspended wait: try_wait with a long suspend-time hint parks the warp until the phase completes -- no polling
+// traffic on the shared-memory pipe (many warps spinning on try_wait take bandwidth from tensor-core operand reads and
+// bulk copies) and no nanosleep granularity on the wake-up.  Bounded like the others.
+__device__ __forceinline__ void mbar_wait_susp(uint64_t* bar, uint32_t parity) {
+  uint32_t n = 0;
+  while (!mbar_try_wait_t<100000>(bar, parity)) {
+    if (++n > 40000u) {                    // ~4 s of 100 us suspensions
+      printf("nmrgnn_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
 
 
 // One lane of a fully converged warp.  Issuing tcgen05.mma / commit under `if (elect_one())` inside warp-uniform

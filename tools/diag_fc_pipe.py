@@ -37,14 +37,22 @@ def main():
         report(f"pipelined c'={c / 100:.2f}", y, ref)
         report(f"  ... vs round-1 kernel", y, y0)
     h.set_option("fc_pos_comp1_x100", 50)
+    y1 = m(g)
+    h.set_option("fc_pair", 1)
+    yp = m(g)
+    h.set_option("fc_pair", 0)
+    report("pipelined, CTA pairs", yp.astype(np.float64), ref)
+    print("  pair kernel bit-identical to the one-CTA kernel:", bool(np.array_equal(y1, yp)),
+          "max abs diff", float(np.abs(y1 - yp).max()), flush=True)
     # timing: device-resident forward, stage times
     dev = torch.device("cuda", 0)
     n = atoms.shape[0]
     d_in = [torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in g]
     out = torch.empty(n, dtype=torch.float32, device=dev)
     s = int(torch.cuda.current_stream().cuda_stream) or 1
-    for pipe in (0, 1):
+    for pipe, pair in ((0, 0), (1, 0), (1, 1)):
         h.set_option("fc_pipe", pipe)
+        h.set_option("fc_pair", pair)
         h.set_option("profile", 1)
         ts = []
         for it in range(8):
@@ -53,13 +61,17 @@ def main():
             st = h.stage_times()
             ts.append([st["edge"], st["embed"]] + list(st["mp_layers"]) + [st["fc_readout"]])
         t = np.median(np.array(ts[3:]), axis=0)
-        print(f"fc_pipe={pipe}: stage ms {np.round(t, 4).tolist()} total {t.sum():.4f}", flush=True)
+        print(f"fc_pipe={pipe} fc_pair={pair}: stage ms {np.round(t, 4).tolist()} total {t.sum():.4f}", flush=True)
         h.set_option("profile", 0)
-    h.set_option("fc_role_counters", 1)
-    h.forward(d_in[0], d_in[1], d_in[2], d_in[3], n, 16, out, _capi.MEM_DEVICE, s)
-    h.synchronize(s)
-    h.set_option("fc_role_counters", 2)
-    h.set_option("fc_role_counters", 0)
+    for pair in (0, 1):
+        h.set_option("fc_pair", pair)
+        h.set_option("fc_role_counters", 1)
+        h.forward(d_in[0], d_in[1], d_in[2], d_in[3], n, 16, out, _capi.MEM_DEVICE, s)
+        h.synchronize(s)
+        print(f"fc_pair={pair}:", end=" ", flush=True)
+        h.set_option("fc_role_counters", 2)
+        h.set_option("fc_role_counters", 0)
+    h.set_option("fc_pair", 0)
 
 
 if __name__ == "__main__":
