@@ -525,6 +525,11 @@ def test_pipelined_node_mlp_kernel(model, config2_batch):
             assert np.array_equal(ys[pipe] == 0, ref64 == 0)
         assert not np.array_equal(ys[0], ys[1])
         h.set_option("fc_pipe", 1)
+        # CTA-pair form of the pipelined kernel (cta_group::2, odd tile count: the last pair has an empty tile): same bits
+        h.set_option("fc_pair", 1)
+        assert np.array_equal(model((atoms, nlist, edges, inv)), ys[1])
+        assert np.array_equal(model(take_graphs(config2_batch, np.array([3]))[:4]), ys[1][int(offs[3]):int(offs[4])])
+        h.set_option("fc_pair", 0)
         sub = take_graphs(config2_batch, np.array([11, 40]))          # other tile positions, partial last tile
         a, b = int(offs[11]), int(offs[12])
         assert np.array_equal(model(sub[:4])[: b - a], ys[1][a:b])
@@ -554,6 +559,7 @@ def test_pipelined_node_mlp_kernel(model, config2_batch):
         assert np.allclose(out[2], out[0] + out[1], rtol=2e-6, atol=2e-5)
     finally:
         h.set_option("fc_pipe", 1)
+        h.set_option("fc_pair", 0)
         h.set_option("tc_min_atoms", 1024)
 
 

@@ -1,6 +1,6 @@
 """Small forward calls for compute-sanitizer (memcheck / racecheck / synccheck): the reference's unit-test ring graph and
 a 300-atom protein fragment through every compute path (exact-FP32 kernels, tensor-core kernels forced on the small
-call, edge MLP instead of the table, column-split MP pairs), each checked against its golden peaks.
+call -- the pipelined node MLP is their default --, edge MLP instead of the table, column-split MP pairs), each checked against its golden peaks.
 Usage:  compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
 import os
 import sys
@@ -29,13 +29,15 @@ def main():
                             ("tcgen05 + edge MLP", {"tc_min_atoms": 0, "edge_table": 0}),
                             ("tcgen05, column-split MP pairs", {"tc_min_atoms": 0, "mp_nsplit": 1}),
                             ("tcgen05, 2 chain segments", {"tc_min_atoms": 0, "mp_chain_segments": 2}),
-                            ("tcgen05, single accumulator", {"tc_min_atoms": 0, "mp_single_acc": 1})):
+                            ("tcgen05, single accumulator", {"tc_min_atoms": 0, "mp_single_acc": 1}),
+                            ("tcgen05, round-1 node MLP", {"tc_min_atoms": 0, "fc_pipe": 0}),
+                            ("tcgen05, node MLP on CTA pairs", {"tc_min_atoms": 0, "fc_pair": 1})):
             for k, v in opts.items():
                 h.set_option(k, v)
             y = m(graph)
             print(f"{name:14s} {label:34s} path {h.compute_path:40s} tol_ratio {tol_ratio(y, g['peaks_f64']):.3f}", flush=True)
             for k in opts:
-                h.set_option(k, {"tc_min_atoms": 1024, "edge_table": 1, "mp_chain_segments": 1}.get(k, 0))
+                h.set_option(k, {"tc_min_atoms": 1024, "edge_table": 1, "mp_chain_segments": 1, "fc_pipe": 1}.get(k, 0))
     # GPU graph builder: cell list and brute force on a 900-atom fragment, two graphs in one call
     from nmrgnn_b200 import _capi
     from conftest import GOLDEN
