@@ -216,6 +216,9 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *                  truncating accumulation steps per output: max error on config 2 0.83 instead of 0.53 of the tolerance
  *                  (default 0);
  *   "mp_pos_comp1_x100" = v: slope of that kernel's position-dependent compensation (default 55);
+ *   "mp_l1_prefetch" = 1: the MP kernel's record-loader warp prefetches the tile's own node rows into L1 one feature
+ *                  pass ahead of the producers (default 1; a pure hint, no effect on results: -1 % launch time, -4 % with
+ *                  "mp_single_acc");
  *   "mp_nsplit" = 1: run the MP layers on column-split CTA pairs (kernels_mp_nsplit.cuh: two CTAs of a cluster share one
  *                  128-atom tile, each owns 128 output columns and gathers 64 rows; double-buffered accumulators) --
  *                  bit-identical results, measured slower than the one-CTA kernel (0.45 vs 0.37 ms); default 0;

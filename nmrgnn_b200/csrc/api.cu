@@ -119,6 +119,7 @@ struct nmrgnn_handle {
   bool compensate = true;
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
+  bool mp_l1_prefetch = true;           // option "mp_l1_prefetch"
   bool mp_nsplit = false;               // option "mp_nsplit": MP layers by column-split CTA pairs (kernels_mp_nsplit.cuh)
   int mp_nseg = 1;                      // option "mp_chain_segments": accumulation chains per MP tile (kernels_tc.cuh)
   // edge block as a create-time FP64 table of the scalar function d -> EdgeFC(RBF(d)) (edge_table.cuh)
@@ -717,6 +718,7 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   a.nseg = h->mp_nseg;
   a.hmax_pair = in_pair;
   a.dbg = h->mp_dbg;
+  a.l1_prefetch = h->mp_l1_prefetch ? 1 : 0;
   const int64_t tiles = (n + 127) / 128;
   const bool nsplit = h->mp_nsplit && a.nseg == 1 && !in_pair_unsupported(h);
   if (out_pair) *out_pair = nsplit ? 1 : 0;
@@ -1958,6 +1960,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
       if (int rc = pack_mp_images(h)) return rc;
       return calibrate_mp(h);
     }
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_l1_prefetch") == 0) {
+    h->mp_l1_prefetch = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_nsplit") == 0) {

@@ -884,6 +884,7 @@ __global__ void __launch_bounds__(256) row_absmax256_kernel(const float* __restr
 //   warps 4-7: epilogue (thread = atom row)                warps 8-15: producers
 // ----------------------------------------------------------------------------------
 struct MpTcArgs {
+  int l1_prefetch;           // option "mp_l1_prefetch": warp 2 prefetches the tile's own node rows into L1 one pass ahead
   const float* h_in;         // [n_atoms, 256]
   const float* hmax_in;      // [n_atoms]  max_l |h_in[i,l]|
   float* h_out;              // [n_atoms, 256]
@@ -1020,6 +1021,27 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         for (int i = lane; i < nrows * 8; i += 32) tc::prefetch_l2(hb + (size_t)i * 128);
         const char* rb = reinterpret_cast<const char*>(p.rec + b0 * K);
         for (int i = lane; i * 128 < nrows * K * 16; i += 32) tc::prefetch_l2(rb + (size_t)i * 128);
+      }
+      if (p.l1_prefetch) {
+        // L1 prefetch of the tile's OWN node rows, one feature pass ahead of the producers: for chain-ordered molecules
+        // most neighbours of a tile's atoms are atoms of the tile, so these 128 lines per pass are the largest group of
+        // compulsory L1 misses of the gather (every (row, pass) line is first touched exactly once).  Paced on the
+        // producers' a_full barriers with a BOUNDED poll: this warp must never block on the producers, who wait for
+        // its next record copy.
+        const int64_t a0 = tile * 128;
+        const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
+        const char* hb = reinterpret_cast<const char*>(p.h_in + a0 * 256);
+        for (int ps = 0; ps < MTC_PASSES; ++ps) {
+          if (ps >= 2) {
+            const uint32_t pk = t * MTC_PASSES + (uint32_t)ps - 2u;        // producers have finished pass ps - 2
+            for (int spin = 0; spin < 64 && !tc::mbar_try_wait(&a_full[pk % AST], (pk / AST) & 1); ++spin) __nanosleep(200);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            if (r < rows) tc::prefetch_l1(hb + (size_t)r * 1024 + (size_t)ps * 128);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -1420,10 +1442,14 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         }
       };
 
+      // K <= 8: the second half-step of every row is all padding -- it is skipped (adding 0 * h is the identity, so the
+      // results are the same bits) and the two register buffers alternate between consecutive rows instead
+      const bool k8 = K <= 8;
       float4 hvA[8], hvB[8];
       load_idx(pw * 4 + rsub, 0, false);
       issue(hvA, 0);                            // first half-step of the tile, in flight during the scale pass
-      load_idx(pw * 4 + rsub, 1, false);
+      if (k8) load_idx(32 + pw * 4 + rsub, 0, false);
+      else load_idx(pw * 4 + rsub, 1, false);
 
       // per-row bound |T[i,.]| <= sum_j max_n|e_ijn| * hmax[nl_ij]  ->  power-of-two scale
       {
@@ -1455,6 +1481,56 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         tc::mbar_wait(&a_empty[st], ((pass / AST) & 1) ^ 1);
         if (p.dbg && warp == 8 && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + (size_t)blockIdx.x * 8 + 5), (unsigned long long)(clock64() - p0));
         const uint32_t ab = ast_a + st * 3 * 16384;
+        // scale, split and store one row's 4 features x E channels into the operand stage
+        auto store_row = [&](int row, const float (&acc)[3][4], float sc) {
+          const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
+                               (((uint32_t)q8 & 1u) << 3);
+#pragma unroll
+          for (int n = 0; n < 3; ++n) {
+            if (n < E) {
+              uint2 hi, lo;
+              if (ONE) {       // lo = x - hi, not scaled by 2^11: it meets the main products in the same accumulator
+                tc::split2_f16_plain(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
+                tc::split2_f16_plain(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
+              } else {
+                tc::split2_f16(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
+                tc::split2_f16(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
+              }
+              tc::sts64(ab + n * 16384 + off, hi.x, hi.y);
+              tc::sts64(ab + n * 16384 + 8192 + off, lo.x, lo.y);
+            }
+          }
+        };
+        if (k8) {
+          // entering: hvA holds (row of step 0, slots 0..7) in flight, nidx the indices of the row of step 1
+#pragma unroll 1
+          for (int step = 0; step < 4; step += 2) {
+            const int row0 = step * 32 + pw * 4 + rsub, row1 = row0 + 32;
+            const bool last = step == 2;
+            const int nrow = last ? pw * 4 + rsub : row1 + 32;          // the row after row1 ...
+            const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);    // ... in this pass or the next one
+            const int nrow2 = nrow + 32;                                // and the one after that (indices only)
+            float acc[3][4];
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
+            float sc = tc::lds32f(fs_a + (uint32_t)row0 * 4u);
+            issue(hvB, ps);                     // row1
+            load_idx(nrow, 0, false);
+            consume(hvA, row0, 0, acc, false);
+            store_row(row0, acc, sc);
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
+            sc = tc::lds32f(fs_a + (uint32_t)row1 * 4u);
+            issue(hvA, nps);                    // nrow
+            load_idx(nrow2, 0, false);
+            consume(hvB, row1, 0, acc, false);
+            store_row(row1, acc, sc);
+          }
+        } else {
 #pragma unroll 1
         for (int step = 0; step < 4; ++step) {
           const int row = step * 32 + pw * 4 + rsub;
@@ -1484,23 +1560,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
             load_idx(nrow, 1, false);
             consume(hvB, row, 1, acc, false);
           }
-          const uint32_t off = (uint32_t)row * 64u + ((((uint32_t)q8 >> 1) ^ (((uint32_t)row >> 1) & 3u)) << 4) +
-                               (((uint32_t)q8 & 1u) << 3);
-#pragma unroll
-          for (int n = 0; n < 3; ++n) {
-            if (n < E) {
-              uint2 hi, lo;
-              if (ONE) {       // lo = x - hi, not scaled by 2^11: it meets the main products in the same accumulator
-                tc::split2_f16_plain(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
-                tc::split2_f16_plain(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
-              } else {
-                tc::split2_f16(acc[n][0] * sc, acc[n][1] * sc, hi.x, lo.x);
-                tc::split2_f16(acc[n][2] * sc, acc[n][3] * sc, hi.y, lo.y);
-              }
-              tc::sts64(ab + n * 16384 + off, hi.x, hi.y);
-              tc::sts64(ab + n * 16384 + 8192 + off, lo.x, lo.y);
-            }
-          }
+          store_row(row, acc, sc);
+        }
         }
         tc::fence_proxy_async();
         __syncwarp();
