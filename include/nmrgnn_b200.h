@@ -197,6 +197,9 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *   "force_ffma" = 1: use the exact-FP32 FFMA kernels even where the tcgen05 path applies;
  *   "edge_table" = 0: evaluate the edge block (RBF -> EdgeFCBlock) with the MLP kernels (tcgen05 / FFMA) for every
  *                  edge instead of the create-time table (default 1 where the table exists, see nmrgnn_edge_table_info);
+ *   "knn_warp" = 0: the cell-list search of nmrgnn_knn_graph by eight threads per query atom with per-thread lists in
+ *                  shared memory and a merge (round-2 first form) instead of one warp per query atom with the sorted
+ *                  list in registers (default 1; identical output);
  *   "knn_cells" = 0: nmrgnn_knn_graph searches every atom of the graph per query (brute force) instead of the cell list
  *                  (default 1; identical output);
  *   "fc_pipe" = 0: node MLP + readout on the round-1 kernel (MMA and epilogue phases alternate on the resident tile; main

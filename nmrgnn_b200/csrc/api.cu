@@ -71,6 +71,7 @@ struct nmrgnn_handle {
   bool force_ffma = false;
   DevBuf pos, offs, knn_sorted, knn_cells, knn_grid;   // kNN builder: positions, offsets, cell-list workspaces
   bool knn_cells_on = true;             // option "knn_cells": cell-list search (default) / brute force
+  bool knn_warp = true;                 // option "knn_warp": cell-list query by one warp per atom (default) / 8 threads
   std::vector<int64_t> offs_cached;     // graph_offsets currently resident in `offs` (skips the upload when unchanged:
                                         // a frame stream repeats the same offsets, and the call stays graph-capturable)
   // tensor-core path (F=256, H=128, E<=8): pre-split, pre-swizzled operand images
@@ -1908,6 +1909,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
     h->fc_rz = 1.0f + (float)value / 10.0f / 16777216.0f;
     return NMRGNN_OK;
   }
+  if (std::strcmp(name, "knn_warp") == 0) {
+    h->knn_warp = value != 0;
+    return NMRGNN_OK;
+  }
   if (std::strcmp(name, "knn_cells") == 0) {
     h->knn_cells_on = value != 0;
     return NMRGNN_OK;
@@ -2088,13 +2093,18 @@ int nmrgnn_knn_graph(nmrgnn_handle* h, const float* positions, const int64_t* gr
     b.sorted = (float4*)h->knn_sorted.p;
     b.cell_start = (uint32_t*)h->knn_cells.p;
     b.grid = (KnnGrid*)h->knn_grid.p;
+    b.k = k;
     knn_build_cells_kernel<<<(unsigned)n_graphs, KNN_BUILD_THREADS, 0, s>>>(b);
     KnnQueryArgs qa{};
     qa.out = a;
     qa.sorted = b.sorted;
     qa.cell_start = b.cell_start;
     qa.grid = b.grid;
-    knn_query_cells_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(qa);
+    const int64_t chunks_w = (max_n + KNN_WARP_QPB - 1) / KNN_WARP_QPB;
+    if (h->knn_warp && chunks_w <= 65535)      // one warp per query atom (grid.y limit: graphs up to 262 k atoms)
+      knn_query_warp_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks_w), KNN_THREADS, 0, s>>>(qa);
+    else
+      knn_query_cells_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(qa);
     h->launches += 2;
   } else {
     knn_graph_kernel<<<dim3((unsigned)n_graphs, (unsigned)chunks), KNN_THREADS, 0, s>>>(a);

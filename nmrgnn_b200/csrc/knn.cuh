@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_graph_kernel(const KnnArgs p)
 // ----------------------------------------------------------------------------------------------------------------
 constexpr int KNN_MAX_CELLS = 8192;
 constexpr int KNN_BUILD_THREADS = 1024;
-constexpr float KNN_ATOMS_PER_CELL = 6.0f;   // of the bounding box; dense regions of a protein hold 2-3x that
+// Atoms per cell OF THE BOUNDING BOX.  The 3 x 3 x 3 block around a query is final once the k-th distance is below the cell
+// size c, i.e. once a sphere of radius c holds k atoms: 4.19 c^3 rho >= k, about k / 4 atoms per OCCUPIED cell; a protein
+// fills a quarter to a half of its bounding box, hence k / 12.  (Round 2 started with 6 for every k: cells twice too
+// wide, 43 x more candidates in the block than in the sphere that matters.)  Any value is exact -- the block grows.
+__host__ __device__ __forceinline__ float knn_atoms_per_cell(int k) { return fmaxf(0.5f, (float)k * (1.0f / 12.0f)); }
 
 struct KnnGrid {
   float ox, oy, oz, inv_c;
@@ -168,6 +172,7 @@ struct KnnCellArgs {
   float4* sorted;            // [n_atoms] atoms of every graph in cell order
   uint32_t* cell_start;      // [n_graphs][KNN_MAX_CELLS + 1]
   KnnGrid* grid;             // [n_graphs]
+  int k;
 };
 
 __device__ __forceinline__ int knn_cell_coord(float x, float o, float inv_c, int n) {
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(KNN_BUILD_THREADS) knn_build_cells_kernel(cons
       l[d] = a;
       e[d] = fmaxf(b - a, 1e-3f);
     }
-    float c = cbrtf(KNN_ATOMS_PER_CELL * e[0] * e[1] * e[2] / (float)n);
+    float c = cbrtf(knn_atoms_per_cell(p.k) * e[0] * e[1] * e[2] / (float)n);
     c = fmaxf(c, 0.05f);
     int nx, ny, nz;
     for (;;) {
@@ -447,6 +452,118 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_cells_kernel(const KnnQ
     done = __shfl_sync(gmask, done, lane & 24);
     if (done) return;
     __syncwarp(gmask);     // the merge buffers are reused by the next, larger block
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Cell-list query, one WARP per query atom (round 2, the default): the eight-threads-per-query kernel above executes
+// 36 k warp instructions per warp of four queries -- their row scans and list insertions diverge, every lane keeps its
+// own sorted list in shared memory and one lane in eight merges them, twice.  Here the 32 lanes of a warp read 32
+// consecutive candidates of a cell row (coalesced float4), and the ONE sorted list of the query lives in registers, entry
+// l in lane l (k <= 32): a candidate that beats the current k-th entry is broadcast, every lane compares it with its
+// entry, the insert position is a popcount of a ballot and the tail moves up by one shuffle.  No shared memory, no
+// divergence between queries, no merge.  Same block walk, same distance expression, same (distance^2, index) order
+// as the kernels above: the output is the same bits.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int KNN_WARP_QPB = KNN_THREADS / 32;      // query atoms per block
+
+__global__ void __launch_bounds__(KNN_THREADS) knn_query_warp_kernel(const KnnQueryArgs a) {
+  const KnnArgs& p = a.out;
+  const int g = blockIdx.x;
+  const int64_t a0 = p.offsets[g];
+  const int n = (int)(p.offsets[g + 1] - a0);
+  const int lane = threadIdx.x & 31;
+  const int q_local = blockIdx.y * KNN_WARP_QPB + (threadIdx.x >> 5);
+  if (q_local >= n) return;                                     // (whole warps)
+  const KnnGrid G = a.grid[g];
+  const uint32_t* cs = a.cell_start + (size_t)g * (KNN_MAX_CELLS + 1);
+  const float4* sp = a.sorted + a0;
+  const float* q = p.pos + (a0 + q_local) * 3;
+  const float qx = q[0], qy = q[1], qz = q[2];
+  const int cx = knn_cell_coord(qx, G.ox, G.inv_c, G.nx), cy = knn_cell_coord(qy, G.oy, G.inv_c, G.ny),
+            cz = knn_cell_coord(qz, G.oz, G.inv_c, G.nz);
+  const int k = p.k;
+  const int64_t row = (a0 + q_local) * k;
+  float ed = 3.4e38f;          // this lane's entry of the sorted list (lanes >= count: unused)
+  int ei = 0x7fffffff;
+  int count = 0;               // warp-uniform
+  int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;     // the block already scanned (empty)
+  // 32 consecutive candidates of the sorted order: distance, prefilter, insertions
+  auto scan = [&](int s0, int s1) {
+    for (int base = s0; base < s1; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < s1;
+      const float4 c = sp[valid ? i : s0];
+      const float dx = __fsub_rn(c.x, qx), dy = __fsub_rn(c.y, qy), dz = __fsub_rn(c.z, qz);
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      const int j = __float_as_int(c.w);
+      bool cand = valid && j != q_local && !(p.cutoff2 > 0.f && d2 > p.cutoff2);
+      if (count == k) {        // (uniform) prefilter against the current k-th entry
+        const float wd = __shfl_sync(0xffffffffu, ed, k - 1);
+        const int wi = __shfl_sync(0xffffffffu, ei, k - 1);
+        cand = cand && knn_before(d2, j, wd, wi);
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, cand);
+      while (mask) {           // (uniform) one insertion per surviving candidate
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float cd = __shfl_sync(0xffffffffu, d2, src);
+        const int cj = __shfl_sync(0xffffffffu, j, src);
+        if (count == k) {      // the list may have tightened since the prefilter
+          const float wd = __shfl_sync(0xffffffffu, ed, k - 1);
+          const int wi = __shfl_sync(0xffffffffu, ei, k - 1);
+          if (!knn_before(cd, cj, wd, wi)) continue;
+        }
+        const int pos = __popc(__ballot_sync(0xffffffffu, lane < count && knn_before(ed, ei, cd, cj)));
+        const float ud = __shfl_up_sync(0xffffffffu, ed, 1);
+        const int ui = __shfl_up_sync(0xffffffffu, ei, 1);
+        if (lane > pos && lane < k) {
+          ed = ud;
+          ei = ui;
+        }
+        if (lane == pos) {
+          ed = cd;
+          ei = cj;
+        }
+        if (count < k) ++count;
+      }
+    }
+  };
+  for (int r = 1;; ++r) {
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, G.nx - 1), y0 = max(cy - r, 0), y1 = min(cy + r, G.ny - 1),
+              z0 = max(cz - r, 0), z1 = min(cz + r, G.nz - 1);
+    // only the shell that the previous, smaller block did not cover is scanned; the list carries over
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        // cells x0 .. x1 of a row are contiguous in the sorted order
+        const int rb = (z * G.ny + y) * G.nx;
+        if (z >= pz0 && z <= pz1 && y >= py0 && y <= py1) {
+          if (x0 < px0) scan((int)cs[rb + x0], (int)cs[rb + px0]);
+          if (x1 > px1) scan((int)cs[rb + px1 + 1], (int)cs[rb + x1 + 1]);
+        } else {
+          scan((int)cs[rb + x0], (int)cs[rb + x1 + 1]);
+        }
+      }
+    px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+    const bool whole = x0 == 0 && y0 == 0 && z0 == 0 && x1 == G.nx - 1 && y1 == G.ny - 1 && z1 == G.nz - 1;
+    const float dk = __shfl_sync(0xffffffffu, ed, k - 1);
+    // (0.9999: the cell of a point is floor((x - o) / c) in float32, so a cell boundary is only exact to a few ulp)
+    const float reach = __fmul_rn(__fmul_rn((float)r, G.c), 0.9999f);
+    const float lim2 = __fmul_rn(reach, reach);
+    // with a cutoff nothing beyond it matters: the block is sufficient once it reaches the cutoff
+    const bool cut_ok = p.cutoff2 > 0.f && lim2 > p.cutoff2;
+    if (whole || cut_ok || (count == k && dk < lim2)) {
+      const bool have = lane < count;
+      const int j = have ? ei : 0;
+      // library.py:115-116 counts nlist > 0 (a real neighbour with index 0 is not counted)
+      const int deg = __popc(__ballot_sync(0xffffffffu, have && j > 0));
+      if (lane < k) {
+        p.nlist[row + lane] = (int32_t)(a0 + j);
+        p.edges[row + lane] = have ? sqrtf(ed) : 0.0f;
+      }
+      if (lane == 0) p.inv_degree[a0 + q_local] = deg > 0 ? __fdiv_rn(1.0f, (float)deg) : 0.0f;
+      return;
+    }
   }
 }
 

@@ -367,14 +367,18 @@ def test_knn_cell_list_equals_brute_force(model):
         offs = np.concatenate([[0], np.cumsum([len(g) for g in graphs])]).astype(np.int64)
         n = allpos.shape[0]
         res = {}
-        for mode in (1, 0):
-            h.set_option("knn_cells", mode)
+        # cell list by one warp per query atom (the default), by eight threads per query atom, brute force
+        for mode, (cells, warp) in enumerate(((1, 1), (1, 0), (0, 0))):
+            h.set_option("knn_cells", cells)
+            h.set_option("knn_warp", warp)
             nl, ed, inv = np.empty((n, k), np.int32), np.empty((n, k), np.float32), np.empty(n, np.float32)
             h.knn_graph(allpos, offs, n, len(graphs), k, cutoff, nl, ed, inv, _capi.MEM_HOST)
             res[mode] = (nl, ed, inv)
         h.set_option("knn_cells", 1)
-        for a, b in zip(res[1], res[0]):
-            assert np.array_equal(a, b), (len(graphs), k, cutoff)
+        h.set_option("knn_warp", 1)
+        for other in (0, 1):
+            for a, b in zip(res[other], res[2]):
+                assert np.array_equal(a, b), (other, len(graphs), k, cutoff)
 
 
 def test_tcgen05_selftest_gemm(model):
