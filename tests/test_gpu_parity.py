@@ -785,6 +785,36 @@ def test_second_weight_set_on_tensor_cores_against_oracle():
             m.close()
 
 
+def test_many_element_classes_on_tensor_cores():
+    """num_elem beyond what the pipelined node-MLP kernel keeps in flight (16 classes) falls back to the round-1 kernel's
+    readout; 10, 16, 20 and 40 classes at the pretrained geometry on the tensor-core kernels against the fp64 oracle
+    (the reference allows up to 100 element classes, model.py:222)."""
+    import nmrgnn_b200
+    from nmrgnn_b200 import workloads
+    from oracle import forward as orc
+    rng = np.random.default_rng(9)
+    for num_elem in (10, 16, 20, 40):
+        std = np.zeros(num_elem, np.float32)
+        avg = np.zeros(num_elem, np.float32)
+        std[1:] = rng.uniform(0.5, 30.0, num_elem - 1).astype(np.float32)
+        avg[1:] = rng.uniform(1.0, 120.0, num_elem - 1).astype(np.float32)
+        m = nmrgnn_b200.build_GNNModel(dict(atom_feature_size=256, edge_feature_size=3, edge_hidden_size=128, mp_layers=4,
+                                            fc_layers=4, edge_fc_layers=4, mp_activation="softplus", fc_activation="softplus"),
+                                       num_elem=num_elem, seed=30 + num_elem, peak_std=std, peak_avg=avg)
+        try:
+            m.handle.set_option("tc_min_atoms", 0)
+            atoms10, nlist, edges, inv = workloads.protein_graph(5, neighbor_number=16)
+            n = atoms10.shape[0]
+            atoms = np.zeros((n, num_elem), np.float32)
+            atoms[np.arange(n), rng.integers(1, num_elem, n)] = 1.0
+            ref = orc.forward(m.params, atoms, nlist, edges, inv, dtype=np.float64)
+            r = tol_ratio(m((atoms, nlist, edges, inv)), ref)
+            print(f"num_elem {num_elem}: tensor cores {r:.3f} (path {m.handle.compute_path})")
+            assert r <= 1.0
+        finally:
+            m.close()
+
+
 def test_bad_index_detected_on_both_routes(any_model):
     """An out-of-range neighbour index raises IndexError (TF's CPU GatherV2 raises too) on the tensor-core route
     (index check inside the edge kernel, chunked or not) and on the exact-FP32 route; the handle stays usable."""
