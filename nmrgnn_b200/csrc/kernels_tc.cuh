@@ -912,6 +912,14 @@ struct MpTcArgs {
 // running sum is parked in the tile's own rows of h_out (written and re-read by the same thread; L2-resident) -- and
 // the next chain starts from a cleared accumulator.  The producers keep filling the operand ring during a drain.
 constexpr int MTC_THREADS = 512;
+// Register budget per warpgroup (setmaxnreg).  The kernel as a whole sits at the 128 registers 512 threads allow, with no
+// slack: two harmless additions (two griddepcontrol instructions; a variable trip count of the producers' step loop)
+// each pushed a few bytes into local memory inside the gather loop and cost 3-4 %.  The light warpgroup (W' loader, MMA
+// issuer, record loader, an idle warp) gives up most of its registers and the three heavy ones (epilogue, producers)
+// take them: 4 x 32 x 40 + 12 x 32 x 152 = 63 488.  An increase is served only from registers released inside the CTA,
+// every warp of a warpgroup must execute the SAME setmaxnreg instruction, and ptxas budgets the code a setmaxnreg
+// dominates -- hence one at the head of each warpgroup's branch.
+constexpr int MTC_REGS_LIGHT = 64, MTC_REGS_HEAVY = 144;
 constexpr int MTC_PASSES = 8;          // 256 / 32
 constexpr int MTC_BRING = 4;           // W' ring: slots of 16 KB, the hi and the lo image of a (pass, n) chunk are separate slots
 constexpr int MTC_BSLOT = 16384;
@@ -980,6 +988,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   const int64_t tile_step = (int64_t)gridDim.x;
   const int64_t tile_end = n_tiles;
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MTC_REGS_LIGHT));
   if (warp == 0) {
     // ===================== W' loader =====================
     if (lane == 0) {
@@ -1134,7 +1144,9 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         o[3] = w_b;              //   waiting for W' (b_full)
       }
     }
+  }
   } else if (warp >= 4 && warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MTC_REGS_HEAVY));
     // ===================== epilogue =====================
     // TMEM hands every thread one atom row; global memory wants 128 contiguous bytes per row and
     // instruction.  Each group of 8 lanes therefore transposes its 8 rows x 8 float4 block with
@@ -1372,6 +1384,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
       if (grow + gi < rows) p.hmax_out[a0 + grow + gi] = mine;
     }
   } else if (warp >= 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MTC_REGS_HEAVY));
     // ===================== producers: gather-aggregate, scale, split =====================
     const int pw = warp - 8;                 // 0..7
     const int ptid = tid - 256;              // 0..255
