@@ -1146,7 +1146,9 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     }
   }
   } else if (warp >= 4 && warp < 8) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MTC_REGS_HEAVY));
+    // (the single-accumulator kernel runs best with 160 registers in the epilogue: 0.330 against 0.340 ms; the default
+    //  kernel spills there)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ONE ? 160 : MTC_REGS_HEAVY));
     // ===================== epilogue =====================
     // TMEM hands every thread one atom row; global memory wants 128 contiguous bytes per row and
     // instruction.  Each group of 8 lanes therefore transposes its 8 rows x 8 float4 block with
