@@ -219,6 +219,9 @@ int nmrgnn_edge_table_info(nmrgnn_handle* h, int32_t* n_intervals, double* rel_e
  *                  truncating accumulation steps per output: max error on config 2 0.83 instead of 0.53 of the tolerance
  *                  (default 0);
  *   "mp_pos_comp1_x100" = v: slope of that kernel's position-dependent compensation (default 55);
+ *   "mp_small_tiles" = 0: MP-layer tiles are always 128 atoms (default 1: a call of less than one wave of 128-atom
+ *                  tiles -- fewer than 148 x 128 atoms -- runs on tiles of 32 / 64 / 96 atoms spread over more SMs; same
+ *                  results, lower latency for single structures);
  *   "mp_l1_prefetch" = 1: the MP kernel's record-loader warp prefetches the tile's own node rows into L1 one feature
  *                  pass ahead of the producers (default 1; a pure hint, no effect on results: -1 % launch time, -4 % with
  *                  "mp_single_acc");

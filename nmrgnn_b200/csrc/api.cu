@@ -121,6 +121,7 @@ struct nmrgnn_handle {
   long long* mp_dbg = nullptr;          // diagnostics: per-CTA role cycle counters of the last MP launch
   int64_t tc_min_atoms = 1024;          // calls smaller than this run on the exact-FP32 kernels
   bool mp_l1_prefetch = true;           // option "mp_l1_prefetch"
+  bool mp_small_tiles = true;           // option "mp_small_tiles": calls of less than one wave run on 32 / 64 / 96-atom tiles
   bool mp_nsplit = false;               // option "mp_nsplit": MP layers by column-split CTA pairs (kernels_mp_nsplit.cuh)
   int mp_nseg = 1;                      // option "mp_chain_segments": accumulation chains per MP tile (kernels_tc.cuh)
   // edge block as a create-time FP64 table of the scalar function d -> EdgeFC(RBF(d)) (edge_table.cuh)
@@ -729,7 +730,19 @@ int launch_mp_tc(nmrgnn_handle* h, cudaStream_t s, int layer, const float* h_in,
   } else if (one) {
     ACT_DISPATCH(a.act, mp_layer_tc1_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
   } else if (a.nseg > 1) ACT_DISPATCH(a.act, mp_layer_tc_seg_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
-  else ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+  else {
+    // less than one wave of 128-atom tiles: smaller tiles on more SMs (a tile's time follows its 32-row steps down to the
+    // MMA + drain floor), e.g. one 2 482-atom protein = 78 tiles of 32 atoms instead of 20 of 128
+    const int64_t per_sm = (n + h->num_sms - 1) / h->num_sms;
+    const int64_t vt_rows = std::max<int64_t>(32, (per_sm + 31) / 32 * 32);
+    if (h->mp_small_tiles && K > 8 && tiles < h->num_sms && vt_rows < 128) {
+      a.vt_rows = (int)vt_rows;
+      a.vt_tiles = (n + vt_rows - 1) / vt_rows;
+      ACT_DISPATCH(a.act, mp_layer_tc_vt_kernel, grid_for(h, a.vt_tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+    } else {
+      ACT_DISPATCH(a.act, mp_layer_tc_kernel, grid_for(h, tiles, 1), MTC_THREADS, MTC_SMEM, s, a);
+    }
+  }
   h->launches++;
   return NMRGNN_OK;
 }
@@ -1352,6 +1365,11 @@ int nmrgnn_create(const nmrgnn_dims* dims, const float* const* weights, int n_we
     for (int l = 0; l < dims->n_mp; ++l) h->mp_w_host[l].assign(weights[w0 + l], weights[w0 + l] + (size_t)F * F * E);
     TRY_RC(pack_mp_images(h));
     ACT_SET_SMEM(mp_layer_tc_kernel, MTC_SMEM);
+    ACT_SET_SMEM(mp_layer_tc_vt_kernel, MTC_SMEM);
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_vt_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_vt_kernel<ACT_SOFTPLUS>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_vt_kernel<ACT_RELU>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
+    CUDA_RC(cudaFuncSetAttribute(mp_layer_tc_vt_kernel<ACT_TANH>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
     ACT_SET_SMEM(mp_layer_tc_seg_kernel, MTC_SMEM);
     ACT_SET_SMEM(mp_layer_tc1_kernel, MTC_SMEM);
     CUDA_RC(cudaFuncSetAttribute(mp_layer_tc1_kernel<ACT_LINEAR>, cudaFuncAttributePreferredSharedMemoryCarveout, 85));
@@ -1965,6 +1983,10 @@ int nmrgnn_set_option(nmrgnn_handle* h, const char* name, int value) {
       if (int rc = pack_mp_images(h)) return rc;
       return calibrate_mp(h);
     }
+    return NMRGNN_OK;
+  }
+  if (std::strcmp(name, "mp_small_tiles") == 0) {
+    h->mp_small_tiles = value != 0;
     return NMRGNN_OK;
   }
   if (std::strcmp(name, "mp_l1_prefetch") == 0) {

@@ -884,6 +884,11 @@ __global__ void __launch_bounds__(256) row_absmax256_kernel(const float* __restr
 //   warps 4-7: epilogue (thread = atom row)                warps 8-15: producers
 // ----------------------------------------------------------------------------------
 struct MpTcArgs {
+  // Variable-tile form (mp_layer_tc_vt_kernel, calls of less than one wave of 128-atom tiles): every tile holds
+  // tile_rows <= 128 atoms (a multiple of 32), so that a small call spreads over more SMs and a tile's producers only
+  // run the 32-row steps it has.  The other kernels ignore these fields (tiles of 128).
+  int64_t vt_tiles;
+  int vt_rows;
   int l1_prefetch;           // option "mp_l1_prefetch": warp 2 prefetches the tile's own node rows into L1 one pass ahead
   const float* h_in;         // [n_atoms, 256]
   const float* hmax_in;      // [n_atoms]  max_l |h_in[i,l]|
@@ -929,9 +934,10 @@ constexpr int MTC_KMAX = 16;
 // feature pass (~38 KB unique per tile) then mostly hit L1.
 constexpr size_t MTC_SMEM = 512 + 2 * 3 * 16384 + MTC_BRING * MTC_BSLOT + 128 * MTC_KMAX * 16 + 2 * 2 * 128 * 4 + 256;
 static_assert(MTC_SMEM + 1024 <= 196 * 1024, "MP tensor-core kernel no longer fits the 196 KB shared-memory configuration");
-template <int ACT, bool SEG, bool ONE>
+template <int ACT, bool SEG, bool ONE, bool VT = false>
 __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   static_assert(!(SEG && ONE), "chain segments drain per segment: not combined with the single-accumulator form");
+  static_assert(!VT || (!SEG && !ONE), "variable tiles: default kernel only");
   constexpr int BRING = MTC_BRING;
   constexpr int BSLOT = MTC_BSLOT;
   constexpr bool SPLIT = true;      // one slot = one image (hi or lo) of a (pass, n) chunk
@@ -982,7 +988,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int K = p.K, E = p.E;
-  const int64_t n_tiles = (p.n_atoms + 127) / 128;
+  const int64_t n_tiles = VT ? p.vt_tiles : (p.n_atoms + 127) / 128;
+  const int TR = VT ? p.vt_rows : 128;      // atoms per tile
   // tile walk: the CTA takes tiles blockIdx.x, + gridDim.x, ...
   const int64_t tile_first = (int64_t)blockIdx.x;
   const int64_t tile_step = (int64_t)gridDim.x;
@@ -1015,8 +1022,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     uint32_t t = 0;
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
       if (lane == 0) {
-        const int64_t a0 = tile * 128;
-        const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
+        const int64_t a0 = tile * TR;
+        const int rows = (int)max((int64_t)0, min((int64_t)TR, p.n_atoms - a0));
         const uint32_t bytes = (uint32_t)rows * (uint32_t)K * 16u;
         tc::mbar_wait_relaxed(rec_empty, (t & 1) ^ 1);
         tc::mbar_expect_tx(rec_full, bytes);
@@ -1025,8 +1032,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
       __syncwarp();
       const int64_t nt = tile + tile_step;
       if (nt < n_tiles) {
-        const int64_t b0 = nt * 128;
-        const int nrows = (int)min((int64_t)128, p.n_atoms - b0);
+        const int64_t b0 = nt * TR;
+        const int nrows = (int)min((int64_t)TR, p.n_atoms - b0);
         const char* hb = reinterpret_cast<const char*>(p.h_in + b0 * 256);
         for (int i = lane; i < nrows * 8; i += 32) tc::prefetch_l2(hb + (size_t)i * 128);
         const char* rb = reinterpret_cast<const char*>(p.rec + b0 * K);
@@ -1038,8 +1045,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         // compulsory L1 misses of the gather (every (row, pass) line is first touched exactly once).  Paced on the
         // producers' a_full barriers with a BOUNDED poll: this warp must never block on the producers, who wait for
         // its next record copy.
-        const int64_t a0 = tile * 128;
-        const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
+        const int64_t a0 = tile * TR;
+        const int rows = (int)max((int64_t)0, min((int64_t)TR, p.n_atoms - a0));
         const char* hb = reinterpret_cast<const char*>(p.h_in + a0 * 256);
         for (int ps = 0; ps < MTC_PASSES; ++ps) {
           if (ps >= 2) {
@@ -1167,8 +1174,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
       osc_one = oscale[row] * p.corr;
     }
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
-      const int64_t a0 = tile * 128;
-      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
+      const int64_t a0 = tile * TR;
+      const int rows = (int)max((int64_t)0, min((int64_t)TR, p.n_atoms - a0));
       if (!ONE) tc::mbar_wait(&sc_full[t & 1], (t >> 1) & 1);
       float hm[8];
 #pragma unroll
@@ -1397,8 +1404,8 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
     const float* hq = p.h_in + q8 * 4;
     uint32_t pass = 0, t = 0;
     for (int64_t tile = tile_first; tile < tile_end; tile += tile_step, ++t) {
-      const int64_t a0 = tile * 128;
-      const int rows = (int)max((int64_t)0, min((int64_t)128, p.n_atoms - a0));
+      const int64_t a0 = tile * TR;
+      const int rows = (int)max((int64_t)0, min((int64_t)TR, p.n_atoms - a0));
       float* fs = fscale + (t & 1) * 128;
       float* os = oscale + (t & 1) * 128;
       const uint32_t fs_a = tc::smem_u32(fs);
@@ -1519,9 +1526,9 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
         if (k8) {
           // entering: hvA holds (row of step 0, slots 0..7) in flight, nidx the indices of the row of step 1
 #pragma unroll 1
-          for (int step = 0; step < 4; step += 2) {
+          for (int step = 0; VT ? step * 32 < rows : step < 4; step += 2) {
             const int row0 = step * 32 + pw * 4 + rsub, row1 = row0 + 32;
-            const bool last = step == 2;
+            const bool last = VT ? (step + 2) * 32 >= rows : step == 2;
             const int nrow = last ? pw * 4 + rsub : row1 + 32;          // the row after row1 ...
             const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);    // ... in this pass or the next one
             const int nrow2 = nrow + 32;                                // and the one after that (indices only)
@@ -1547,7 +1554,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
           }
         } else {
 #pragma unroll 1
-        for (int step = 0; step < 4; ++step) {
+        for (int step = 0; VT ? step * 32 < rows : step < 4; ++step) {
           const int row = step * 32 + pw * 4 + rsub;
           float acc[3][4];
 #pragma unroll
@@ -1556,7 +1563,7 @@ __device__ __forceinline__ void mp_layer_tc_body(const MpTcArgs& p) {
             for (int i = 0; i < 4; ++i) acc[n][i] = 0.0f;
           const float sc = tc::lds32f(fs_a + (uint32_t)row * 4u);   // needed only after the FMAs: latency hidden
           // next half-step: next row group of this pass, or the first one of the next pass
-          const bool last = step == 3;
+          const bool last = VT ? (step + 1) * 32 >= rows : step == 3;
           const int nrow = last ? pw * 4 + rsub : row + 32;
           const int nps = min(last ? ps + 1 : ps, MTC_PASSES - 1);   // (the tile's very last prefetch is unused)
           // entering: hvA holds (row, half 0) in flight, nidx the indices of (row, half 1)
@@ -1604,6 +1611,12 @@ __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_kernel(const MpTcA
 // stays in the normal fp16 range), so tensor memory holds two accumulator sets and the epilogue of tile t runs under
 // the MMAs of tile t + 1.  Price: 144 instead of 48 round-toward-zero steps at full magnitude per output (the
 // position-dependent compensation follows the 144-instruction order), error at the level of the exact-FP32 kernels.
+// Variable-tile form for calls of less than one wave (see MpTcArgs): same arithmetic per atom, same bits.
+template <int ACT>
+__global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc_vt_kernel(const MpTcArgs p) {
+  mp_layer_tc_body<ACT, false, false, true>(p);
+}
+
 template <int ACT>
 __global__ void __launch_bounds__(MTC_THREADS, 1) mp_layer_tc1_kernel(const MpTcArgs p) {
   mp_layer_tc_body<ACT, false, true>(p);

@@ -785,6 +785,26 @@ def test_second_weight_set_on_tensor_cores_against_oracle():
             m.close()
 
 
+def test_small_call_tiles_are_bit_identical(model):
+    """Calls of less than one wave of 128-atom tiles run the MP layers on 32 / 64 / 96-atom tiles spread over more SMs
+    (mp_layer_tc_vt_kernel, option mp_small_tiles): same bits as the 128-atom tiling for one protein (32-atom tiles),
+    three proteins (64) and a 300-atom fragment."""
+    from nmrgnn_b200 import workloads
+    h = model.handle
+    cases = [graph_of(load_golden("g108m")), workloads.protein_batch(3, first_seed=4)[:4], graph_of(load_golden("prot300"))]
+    try:
+        h.set_option("tc_min_atoms", 0)
+        for g in cases:
+            h.set_option("mp_small_tiles", 1)
+            y1 = model(g)
+            h.set_option("mp_small_tiles", 0)
+            y0 = model(g)
+            assert np.array_equal(y0, y1)
+    finally:
+        h.set_option("mp_small_tiles", 1)
+        h.set_option("tc_min_atoms", 1024)
+
+
 def test_many_element_classes_on_tensor_cores():
     """num_elem beyond what the pipelined node-MLP kernel keeps in flight (16 classes) falls back to the round-1 kernel's
     readout; 10, 16, 20 and 40 classes at the pretrained geometry on the tensor-core kernels against the fp64 oracle
